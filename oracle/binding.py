@@ -1,0 +1,246 @@
+"""ctypes binding of the CPU oracle (TEST INFRASTRUCTURE -- see vx_oracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs import this module.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "build", "libvx_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(_HERE, "vx_oracle.c"), os.path.join(_HERE, "vx_oracle.h")]
+    stale = force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
+    if stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    return _LIB_PATH
+
+
+class Atlas(C.Structure):
+    _fields_ = [("palette", (C.c_uint32 * 16) * 4), ("indices", (C.c_uint8 * 32) * 4)]
+
+
+class FrameConfig(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("clear_color", C.c_uint32),
+                ("backface_culling", C.c_int32), ("enable_shading", C.c_int32),
+                ("light_dir", C.c_float * 3), ("ambient", C.c_float), ("diffuse", C.c_float),
+                ("n_threads", C.c_int32)]
+
+
+class MeshBatchView(C.Structure):
+    _fields_ = [("quads", C.c_void_p), ("quad_base", C.c_void_p), ("slice_offsets", C.c_void_p),
+                ("face_aabb", C.c_void_p), ("positions", C.c_void_p), ("has_mesh", C.c_void_p),
+                ("n_chunks", C.c_int32)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.vxo_mesh_chunks.restype = C.c_int64
+        _lib.vxo_shade_color_u32.restype = C.c_uint32
+        _lib.vxo_shade_color_u32.argtypes = [C.c_uint32, C.c_float]
+        _lib.vxo_face_light.restype = C.c_float
+        _lib.vxo_texture_sample.restype = C.c_uint32
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def greedy_mesh_slice(mask) -> np.ndarray:
+    mask = np.ascontiguousarray(mask, dtype=np.uint32)
+    assert mask.shape == (32,)
+    out = np.zeros((512, 4), dtype=np.uint8)
+    n = lib().vxo_greedy_mesh_slice(_p(mask), _p(out))
+    return out[:n].copy()
+
+
+def tinyquad_pack(u, v, w, h, bt) -> np.ndarray:
+    out = np.zeros(3, dtype=np.uint8)
+    lib().vxo_tinyquad_pack(C.c_uint8(u), C.c_uint8(v), C.c_uint8(w), C.c_uint8(h), C.c_uint8(bt), _p(out))
+    return out
+
+
+def unpack_quads(q3: np.ndarray) -> np.ndarray:
+    """(n,3) u8 TinyQuads -> (n,5) [u, v, w, h, block_type]  (mesh.rs:309-341)."""
+    q3 = np.asarray(q3, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+    u = q3[:, 0] & 0x1F
+    v = ((q3[:, 0] >> 5) & 7) | ((q3[:, 1] & 3) << 3)
+    w = ((q3[:, 1] >> 2) & 0x3F) + 1
+    h = (q3[:, 2] & 0x3F) + 1
+    bt = (q3[:, 2] >> 6) & 3
+    return np.stack([u, v, w, h, bt], axis=1)
+
+
+class MeshBatch:
+    """Host-side mesh batch in the same layout the product ABI returns."""
+
+    def __init__(self, quads, quad_base, quad_count, slice_offsets, face_aabb, has_mesh, positions):
+        self.quads = quads
+        self.quad_base = quad_base
+        self.quad_count = quad_count
+        self.slice_offsets = slice_offsets
+        self.face_aabb = face_aabb
+        self.has_mesh = has_mesh
+        self.positions = np.ascontiguousarray(positions, dtype=np.int32)
+
+    @property
+    def n_chunks(self):
+        return int(self.quad_base.shape[0])
+
+    def chunk_quads(self, i) -> np.ndarray:
+        b, n = int(self.quad_base[i]), int(self.quad_count[i])
+        return self.quads[3 * b:3 * (b + n)].reshape(-1, 3)
+
+    def view(self) -> MeshBatchView:
+        return MeshBatchView(_p(self.quads), _p(self.quad_base), _p(self.slice_offsets), _p(self.face_aabb),
+                             _p(self.positions), _p(self.has_mesh), self.n_chunks)
+
+
+def mesh_chunks(voxels, neighbors=None, uniform_flags=None, positions=None, cap_quads=None) -> MeshBatch:
+    voxels = np.ascontiguousarray(voxels, dtype=np.uint8).reshape(-1, 32768)
+    n = voxels.shape[0]
+    if neighbors is not None:
+        neighbors = np.ascontiguousarray(neighbors, dtype=np.int32).reshape(n, 6)
+    if uniform_flags is not None:
+        uniform_flags = np.ascontiguousarray(uniform_flags, dtype=np.uint8).reshape(n)
+    if positions is None:
+        positions = np.zeros((n, 3), dtype=np.int32)
+    cap = int(cap_quads) if cap_quads is not None else max(4096, n * 2048)
+    while True:
+        quads = np.zeros(cap * 3, dtype=np.uint8)
+        quad_base = np.zeros(n, dtype=np.uint32)
+        quad_count = np.zeros(n, dtype=np.uint32)
+        so = np.zeros((n, 6, 33), dtype=np.uint32)
+        ab = np.zeros((n, 6, 6), dtype=np.int32)
+        hm = np.zeros(n, dtype=np.uint8)
+        tot = lib().vxo_mesh_chunks(_p(voxels), _p(neighbors), _p(uniform_flags), C.c_int32(n), _p(quads),
+                                    C.c_int64(cap), _p(quad_base), _p(quad_count), _p(so), _p(ab), _p(hm))
+        if tot >= 0:
+            break
+        cap *= 4
+    return MeshBatch(quads[:3 * tot].copy(), quad_base, quad_count, so, ab, hm, positions)
+
+
+def frustum_from_vp(vp) -> np.ndarray:
+    vp = np.ascontiguousarray(vp, dtype=np.float32).reshape(16)
+    planes = np.zeros((6, 4), dtype=np.float32)
+    lib().vxo_frustum_from_vp(_p(vp), _p(planes))
+    return planes
+
+
+def frustum_intersects_aabb(planes, mn, mx) -> bool:
+    planes = np.ascontiguousarray(planes, dtype=np.float32)
+    mn = np.ascontiguousarray(mn, dtype=np.float32)
+    mx = np.ascontiguousarray(mx, dtype=np.float32)
+    return bool(lib().vxo_frustum_intersects_aabb(_p(planes), _p(mn), _p(mx)))
+
+
+def cull_chunks(positions, vp, cam_pos, view_distance, frustum_culling=True) -> np.ndarray:
+    positions = np.ascontiguousarray(positions, dtype=np.int32).reshape(-1, 3)
+    vp = np.ascontiguousarray(vp, dtype=np.float32).reshape(16)
+    cam = np.ascontiguousarray(cam_pos, dtype=np.float32).reshape(3)
+    out = np.zeros(positions.shape[0], dtype=np.uint8)
+    lib().vxo_cull_chunks(_p(positions), C.c_int32(positions.shape[0]), _p(vp), _p(cam), C.c_int32(view_distance),
+                          C.c_int32(1 if frustum_culling else 0), _p(out))
+    return out
+
+
+def horizon_cull(cam_pos, centers, order=None, bins=128, base_margin=0.1, margin_dist_factor=0.05,
+                 min_dist_chunks=2.0) -> np.ndarray:
+    centers = np.ascontiguousarray(centers, dtype=np.float32).reshape(-1, 3)
+    n = centers.shape[0]
+    order = np.arange(n, dtype=np.int32) if order is None else np.ascontiguousarray(order, dtype=np.int32).copy()
+    cam = np.ascontiguousarray(cam_pos, dtype=np.float32).reshape(3)
+    k = lib().vxo_horizon_cull(_p(cam), _p(centers), C.c_int32(order.shape[0]), _p(order), C.c_int32(bins),
+                               C.c_float(base_margin), C.c_float(margin_dist_factor), C.c_float(min_dist_chunks))
+    return order[:k].copy()
+
+
+def default_atlas() -> Atlas:
+    a = Atlas()
+    lib().vxo_default_atlas(C.byref(a))
+    return a
+
+
+def default_frame_config(w, h, n_threads=1) -> FrameConfig:
+    cfg = FrameConfig()
+    lib().vxo_default_frame_config(C.byref(cfg), C.c_int(w), C.c_int(h))
+    cfg.n_threads = n_threads
+    return cfg
+
+
+def render_mesh(mb: MeshBatch, mesh_id, vp, cfg: FrameConfig, atlas: Atlas, rect, color, depth):
+    vp = np.ascontiguousarray(vp, dtype=np.float32).reshape(16)
+    rect = np.ascontiguousarray(rect, dtype=np.int32).reshape(4)
+    v = mb.view()
+    lib().vxo_render_mesh(C.byref(v), C.c_int32(mesh_id), _p(vp), C.byref(cfg), C.byref(atlas), _p(rect),
+                          _p(color), _p(depth))
+
+
+def render_frame(mb: MeshBatch, mesh_ids, vp, cam_pos, cfg: FrameConfig, atlas: Atlas):
+    """Returns (color (H,W) u32, depth (H,W) f32, survivors (k,) i32 in draw order)."""
+    mesh_ids = np.ascontiguousarray(mesh_ids, dtype=np.int32)
+    vp = np.ascontiguousarray(vp, dtype=np.float32).reshape(16)
+    cam = np.ascontiguousarray(cam_pos, dtype=np.float32).reshape(3)
+    color = np.zeros((cfg.height, cfg.width), dtype=np.uint32)
+    depth = np.zeros((cfg.height, cfg.width), dtype=np.float32)
+    surv = np.zeros(max(1, mesh_ids.shape[0]), dtype=np.int32)
+    v = mb.view()
+    k = lib().vxo_render_frame(C.byref(v), _p(mesh_ids), C.c_int32(mesh_ids.shape[0]), _p(vp), _p(cam),
+                               C.byref(cfg), C.byref(atlas), _p(color), _p(depth), _p(surv))
+    return color, depth, surv[:k].copy()
+
+
+def face_basis(face, chunk_pos, slice_idx, vp) -> np.ndarray:
+    vp = np.ascontiguousarray(vp, dtype=np.float32).reshape(16)
+    cp = np.ascontiguousarray(chunk_pos, dtype=np.int32).reshape(3)
+    out = np.zeros((4, 4), dtype=np.float32)
+    lib().vxo_face_basis(C.c_int(face), _p(cp), C.c_uint8(slice_idx), _p(vp), _p(out))
+    return out
+
+
+def basis_project_point(basis, u, v) -> np.ndarray:
+    basis = np.ascontiguousarray(basis, dtype=np.float32)
+    out = np.zeros(4, dtype=np.float32)
+    lib().vxo_basis_project_point(_p(basis), C.c_float(u), C.c_float(v), _p(out))
+    return out
+
+
+def project_packet(basis, u_min, v_min, u_len, v_len):
+    basis = np.ascontiguousarray(basis, dtype=np.float32)
+    arrs = [np.ascontiguousarray(a, dtype=np.uint8) for a in (u_min, v_min, u_len, v_len)]
+    n = arrs[0].shape[0]
+    outs = [np.zeros(n, dtype=np.float32) for _ in range(5)]
+    lib().vxo_project_packet(_p(basis), *[_p(a) for a in arrs], C.c_int(n), *[_p(o) for o in outs])
+    return outs
+
+
+def transform_vertices(verts8, offset, vp) -> np.ndarray:
+    verts8 = np.ascontiguousarray(verts8, dtype=np.uint8).reshape(-1, 8)
+    off = np.ascontiguousarray(offset, dtype=np.float32).reshape(3)
+    vp = np.ascontiguousarray(vp, dtype=np.float32).reshape(16)
+    out = np.zeros((verts8.shape[0], 4), dtype=np.float32)
+    lib().vxo_transform_vertices(_p(verts8), C.c_int32(verts8.shape[0]), _p(off), _p(vp), _p(out))
+    return out
+
+
+def quad_clip_vertices(face, slice_pos, u, v, w, h, chunk_pos, vp) -> np.ndarray:
+    cp = np.ascontiguousarray(chunk_pos, dtype=np.int32).reshape(3)
+    vp = np.ascontiguousarray(vp, dtype=np.float32).reshape(16)
+    out = np.zeros((4, 4), dtype=np.float32)
+    lib().vxo_quad_clip_vertices(C.c_int(face), C.c_uint8(slice_pos), C.c_uint8(u), C.c_uint8(v), C.c_uint8(w),
+                                 C.c_uint8(h), _p(cp), _p(vp), _p(out))
+    return out
