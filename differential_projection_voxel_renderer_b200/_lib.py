@@ -1,0 +1,115 @@
+"""ctypes loader for libvx_b200.so (the C ABI in include/vx_b200.h).
+
+There is no CPU fallback: if the shared library is missing the import of the
+product API raises, and without a CUDA device `Context()` raises VxError
+(VX_ERR_NO_DEVICE).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvx_b200.so")
+
+VX_OK = 0
+VX_ERR_INVALID = -1
+VX_ERR_NO_DEVICE = -2
+VX_ERR_CUDA = -3
+VX_ERR_CAPACITY = -4
+VX_ERR_OOM = -5
+
+NBR_NONE = -1
+NBR_UNIFORM_AIR = -2
+NBR_UNIFORM_SOLID = -3
+
+
+class VxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libvx_b200: {msg} (code {code})")
+        self.code = code
+
+
+class VxAtlas(C.Structure):
+    _fields_ = [("palette", (C.c_uint32 * 16) * 4), ("indices", (C.c_uint8 * 32) * 4)]
+
+
+class VxFrameConfig(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("clear_color", C.c_uint32),
+                ("backface_culling", C.c_int32), ("enable_shading", C.c_int32),
+                ("light_dir", C.c_float * 3), ("ambient", C.c_float), ("diffuse", C.c_float),
+                ("stripe_y0", C.c_int32), ("stripe_rows", C.c_int32),
+                ("differential_projection", C.c_int32), ("async_submit", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
+
+
+class VxMeshBatchInfo(C.Structure):
+    _fields_ = [("n_chunks", C.c_int32), ("n_meshes", C.c_int32), ("total_quads", C.c_int64)]
+
+
+class VxMeshBatchDevice(C.Structure):
+    _fields_ = [("d_quads", C.c_void_p), ("d_quad_base", C.c_void_p), ("d_quad_count", C.c_void_p),
+                ("d_slice_offsets", C.c_void_p), ("d_face_aabb", C.c_void_p), ("d_has_mesh", C.c_void_p),
+                ("d_positions", C.c_void_p)]
+
+
+class VxFrameStats(C.Structure):
+    _fields_ = [("n_input", C.c_int32), ("n_survivors", C.c_int32), ("n_quads", C.c_int32),
+                ("n_triangles", C.c_int32), ("n_bin_entries", C.c_int32), ("n_kernel_launches", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
+
+
+# every symbol include/vx_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+_I = C.c_int32
+PROTOTYPES = {
+    "vx_context_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "vx_context_destroy": (None, [_P]),
+    "vx_error_string": (C.c_char_p, [C.c_int]),
+    "vx_last_error": (C.c_char_p, [_P]),
+    "vx_device_synchronize": (C.c_int, [_P]),
+    "vx_context_stream": (_P, [_P]),
+    "vx_context_launch_count": (C.c_int64, [_P]),
+    "vx_mesh_chunks": (C.c_int, [_P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
+    "vx_mesh_chunks_device": (C.c_int, [_P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
+    "vx_remesh_chunks_device": (C.c_int, [_P, _P, _P, _P, _P]),
+    "vx_mesh_batch_info": (C.c_int, [_P, _P, C.POINTER(VxMeshBatchInfo)]),
+    "vx_mesh_batch_device": (C.c_int, [_P, C.POINTER(VxMeshBatchDevice)]),
+    "vx_mesh_batch_download": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "vx_mesh_batch_upload": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
+    "vx_mesh_batch_release": (None, [_P, _P]),
+    "vx_greedy_mesh_slices": (C.c_int, [_P, _P, _I, _P, _P]),
+    "vx_cull_chunks": (C.c_int, [_P, _P, _I, _P, _P, _I, _I, _P]),
+    "vx_default_frame_config": (None, [C.POINTER(VxFrameConfig), _I, _I]),
+    "vx_default_atlas": (None, [C.POINTER(VxAtlas)]),
+    "vx_set_atlas": (C.c_int, [_P, C.POINTER(VxAtlas)]),
+    "vx_render_frame": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig), _P, _P, _P, C.POINTER(_I)]),
+    "vx_render_frame_device": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig)]),
+    "vx_framebuffer_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I), C.POINTER(_I)]),
+    "vx_frame_stats": (C.c_int, [_P, C.POINTER(VxFrameStats)]),
+    "vx_render_mesh": (C.c_int, [_P, _P, _I, _P, C.POINTER(VxFrameConfig), _P, _P, _P]),
+    "vx_face_basis": (C.c_int, [_P, _P, _P, _P, _I, _P, _P]),
+    "vx_project_packet": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "vx_transform_vertices": (C.c_int, [_P, _P, _I, _P, _P, _P]),
+    "vx_project_mesh_vertices": (C.c_int, [_P, _P, _I, _P, _I, _P, C.c_int64]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libvx_b200.so and bind every prototype.  Raises if the library or a symbol is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()'"
+            " or make -C differential_projection_voxel_renderer_b200/csrc).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

@@ -1,0 +1,446 @@
+"""Host-side mirror of the reference crate's public meshing / rendering API, on top of the C ABI.
+
+Same names and argument meaning as the Rust items they stand in for (citations relative to
+/root/reference/src/): `BinaryGreedyMesher` (meshing/binary_greedy.rs:50-168,675-683), `ChunkMesh` / `TinyQuad`
+(meshing/mesh.rs:273-687), `Framebuffer` (rendering/framebuffer.rs:197-245), `Rasterizer`
+(rendering/rasterizer.rs:335-431), `Frustum` (camera/mod.rs:111-183), `FaceBasis`
+(rendering/differential_projection.rs:18-82), `decompress_and_transform_vertices` (rendering/simd_vertex.rs:24),
+`render_frame` (main.rs:379-608).  Every call runs on the GPU through libvx_b200.so; nothing here falls back to
+the CPU (and nothing here touches oracle/).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import VxAtlas, VxError, VxFrameConfig, VxFrameStats, VxMeshBatchDevice, VxMeshBatchInfo
+
+CHUNK_SIZE = 32
+CHUNK_VOLUME = 32768
+FACE_DIRS = ("PosX", "NegX", "PosY", "NegY", "PosZ", "NegZ")  # mesh.rs:136-143
+
+
+def _p(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One CUDA device + stream (VxContext)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.vx_context_create(int(device), C.byref(h))
+        if rc != 0:
+            raise VxError(rc, self.lib.vx_error_string(rc).decode())
+        self.handle = h
+        self.device = int(device)
+
+    def check(self, rc: int):
+        if rc != 0:
+            detail = self.lib.vx_last_error(self.handle).decode()
+            raise VxError(rc, f"{self.lib.vx_error_string(rc).decode()}: {detail}")
+
+    def synchronize(self):
+        self.check(self.lib.vx_device_synchronize(self.handle))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.vx_context_stream(self.handle) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.vx_context_launch_count(self.handle))
+
+    def set_atlas(self, atlas: VxAtlas):
+        self.check(self.lib.vx_set_atlas(self.handle, C.byref(atlas)))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.vx_context_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def default_frame_config(width: int, height: int) -> VxFrameConfig:
+    cfg = VxFrameConfig()
+    _lib.load().vx_default_frame_config(C.byref(cfg), width, height)
+    return cfg
+
+
+def default_atlas() -> VxAtlas:
+    a = VxAtlas()
+    _lib.load().vx_default_atlas(C.byref(a))
+    return a
+
+
+def unpack_quads(q3: np.ndarray) -> np.ndarray:
+    """(n,3) u8 TinyQuads -> (n,5) [u, v, w, h, block_type]  (TinyQuad accessors, mesh.rs:309-341)."""
+    q3 = np.asarray(q3, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+    u = q3[:, 0] & 0x1F
+    v = ((q3[:, 0] >> 5) & 7) | ((q3[:, 1] & 3) << 3)
+    w = ((q3[:, 1] >> 2) & 0x3F) + 1
+    h = (q3[:, 2] & 0x3F) + 1
+    bt = (q3[:, 2] >> 6) & 3
+    return np.stack([u, v, w, h, bt], axis=1)
+
+
+class ChunkMesh:
+    """Host view of one chunk's mesh (mesh.rs:422-436): 6 FaceLists x 32 slice lists of TinyQuads."""
+
+    def __init__(self, chunk_position, quads, slice_offsets, face_aabb):
+        self.chunk_position = np.asarray(chunk_position, dtype=np.int32)
+        self.quads = quads                    # (n,3) u8 in reference order
+        self.slice_offsets = slice_offsets    # (6,33) u32
+        self.face_aabb = face_aabb            # (6,6) i32: min.xyz, max.xyz
+
+    def quad_count(self) -> int:  # mesh.rs:591
+        return int(self.quads.shape[0])
+
+    def is_empty(self) -> bool:  # mesh.rs:586
+        return self.quad_count() == 0
+
+    def slice_quads(self, face: int, slice_idx: int) -> np.ndarray:
+        a, b = int(self.slice_offsets[face, slice_idx]), int(self.slice_offsets[face, slice_idx + 1])
+        return self.quads[a:b]
+
+    def face_quad_count(self, face: int) -> int:
+        return int(self.slice_offsets[face, 32] - self.slice_offsets[face, 0])
+
+    def world_offset(self) -> np.ndarray:  # mesh.rs:483-485
+        return (self.chunk_position * CHUNK_SIZE).astype(np.float32)
+
+
+class MeshBatch:
+    """Device-resident meshes of a batch of chunks (VxMeshBatch)."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.handle = handle
+        self._host = None
+
+    def info(self) -> VxMeshBatchInfo:
+        info = VxMeshBatchInfo()
+        self.ctx.check(self.ctx.lib.vx_mesh_batch_info(self.ctx.handle, self.handle, C.byref(info)))
+        return info
+
+    def device_pointers(self) -> VxMeshBatchDevice:
+        d = VxMeshBatchDevice()
+        self.ctx.check(self.ctx.lib.vx_mesh_batch_device(self.handle, C.byref(d)))
+        return d
+
+    def download(self):
+        """-> dict of host arrays: quads (Q,3), quad_base, quad_count, slice_offsets (N,6,33), face_aabb (N,6,6), has_mesh."""
+        info = self.info()
+        n, q = info.n_chunks, int(info.total_quads)
+        out = {
+            "quads": np.zeros((q, 3), dtype=np.uint8),
+            "quad_base": np.zeros(n, dtype=np.uint32),
+            "quad_count": np.zeros(n, dtype=np.uint32),
+            "slice_offsets": np.zeros((n, 6, 33), dtype=np.uint32),
+            "face_aabb": np.zeros((n, 6, 6), dtype=np.int32),
+            "has_mesh": np.zeros(n, dtype=np.uint8),
+        }
+        self.ctx.check(self.ctx.lib.vx_mesh_batch_download(
+            self.ctx.handle, self.handle, _p(out["quads"]), _p(out["quad_base"]), _p(out["quad_count"]),
+            _p(out["slice_offsets"]), _p(out["face_aabb"]), _p(out["has_mesh"])))
+        self._host = out
+        return out
+
+    def chunk_quads(self, i: int) -> np.ndarray:
+        h = self._host or self.download()
+        b, c = int(h["quad_base"][i]), int(h["quad_count"][i])
+        return h["quads"][b:b + c]
+
+    def chunk_mesh(self, i: int, position=(0, 0, 0)) -> Optional[ChunkMesh]:
+        h = self._host or self.download()
+        if not h["has_mesh"][i]:
+            return None
+        return ChunkMesh(position, self.chunk_quads(i), h["slice_offsets"][i], h["face_aabb"][i])
+
+    def release(self):
+        if self.handle:
+            self.ctx.lib.vx_mesh_batch_release(self.ctx.handle, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            if self.ctx.handle:
+                self.release()
+        except Exception:
+            pass
+
+
+def upload_mesh_batch(ctx: Context, quads, quad_base, quad_count, slice_offsets, face_aabb, has_mesh, positions) -> MeshBatch:
+    quads = np.ascontiguousarray(quads, dtype=np.uint8).reshape(-1)
+    n = int(np.asarray(quad_base).shape[0])
+    arrs = [np.ascontiguousarray(quad_base, dtype=np.uint32), np.ascontiguousarray(quad_count, dtype=np.uint32),
+            np.ascontiguousarray(slice_offsets, dtype=np.uint32), np.ascontiguousarray(face_aabb, dtype=np.int32),
+            np.ascontiguousarray(has_mesh, dtype=np.uint8), np.ascontiguousarray(positions, dtype=np.int32)]
+    h = C.c_void_p()
+    ctx.check(ctx.lib.vx_mesh_batch_upload(ctx.handle, _p(quads), C.c_int64(quads.size // 3), *[_p(a) for a in arrs], n, C.byref(h)))
+    return MeshBatch(ctx, h)
+
+
+class BinaryGreedyMesher:
+    """binary_greedy.rs:50.  Stateless; methods take an optional Context (default: device 0)."""
+
+    @staticmethod
+    def mesh_batch(voxels, positions=None, neighbors=None, uniform_flags=None, ctx: Optional[Context] = None) -> MeshBatch:
+        """Batched form of mesh_world / mesh_chunk_in_indexed_world (binary_greedy.rs:62-168): N x 32768 voxels."""
+        ctx = ctx or default_context()
+        voxels = np.ascontiguousarray(voxels, dtype=np.uint8).reshape(-1, CHUNK_VOLUME)
+        n = voxels.shape[0]
+        if voxels.size and int(voxels.max()) > 3:
+            raise VxError(_lib.VX_ERR_INVALID, "voxel values must be BlockType 0..3 (block_type.rs:6-11)")
+        positions = None if positions is None else np.ascontiguousarray(positions, dtype=np.int32).reshape(n, 3)
+        neighbors = None if neighbors is None else np.ascontiguousarray(neighbors, dtype=np.int32).reshape(n, 6)
+        uniform_flags = None if uniform_flags is None else np.ascontiguousarray(uniform_flags, dtype=np.uint8).reshape(n)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.vx_mesh_chunks(ctx.handle, _p(voxels), _p(positions), _p(neighbors), _p(uniform_flags), n, C.byref(h)))
+        return MeshBatch(ctx, h)
+
+    @staticmethod
+    def mesh_chunk(voxels, position=(0, 0, 0), ctx: Optional[Context] = None) -> Optional[ChunkMesh]:
+        """binary_greedy.rs:55: no neighbour information, borders are air."""
+        b = BinaryGreedyMesher.mesh_batch(np.asarray(voxels).reshape(1, CHUNK_VOLUME), [position], None, None, ctx)
+        try:
+            return b.chunk_mesh(0, position)
+        finally:
+            b.release()
+
+    @staticmethod
+    def mesh_world(voxels, positions, uniform_flags=None, ctx: Optional[Context] = None):
+        """binary_greedy.rs:62-78: meshes in input order, Uniform / empty chunks skipped; neighbours resolved by position."""
+        positions = np.ascontiguousarray(positions, dtype=np.int32).reshape(-1, 3)
+        index = {tuple(p): i for i, p in enumerate(positions.tolist())}
+        offs = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
+        nb = np.full((positions.shape[0], 6), -1, dtype=np.int32)
+        for i, p in enumerate(positions.tolist()):
+            for f, o in enumerate(offs):
+                j = index.get((p[0] + o[0], p[1] + o[1], p[2] + o[2]))
+                if j is not None:
+                    nb[i, f] = j
+        b = BinaryGreedyMesher.mesh_batch(voxels, positions, nb, uniform_flags, ctx)
+        try:
+            b.download()
+            return [m for m in (b.chunk_mesh(i, positions[i]) for i in range(positions.shape[0])) if m is not None]
+        finally:
+            b.release()
+
+    @staticmethod
+    def greedy_mesh_slice(mask, ctx: Optional[Context] = None) -> np.ndarray:
+        """binary_greedy.rs:675: [u32;32] -> (n,4) u8 quads (x=row, y=col, width, height)."""
+        return BinaryGreedyMesher.greedy_mesh_slices(np.asarray(mask).reshape(1, 32), ctx)[0]
+
+    @staticmethod
+    def greedy_mesh_slices(masks, ctx: Optional[Context] = None):
+        ctx = ctx or default_context()
+        masks = np.ascontiguousarray(masks, dtype=np.uint32).reshape(-1, 32)
+        n = masks.shape[0]
+        out = np.zeros((n, 512, 4), dtype=np.uint8)
+        cnt = np.zeros(n, dtype=np.int32)
+        ctx.check(ctx.lib.vx_greedy_mesh_slices(ctx.handle, _p(masks), n, _p(out), _p(cnt)))
+        return [out[i, :cnt[i]].copy() for i in range(n)]
+
+
+class Frustum:
+    """camera/mod.rs:111-183 evaluated on the device through vx_cull_chunks."""
+
+    def __init__(self, view_projection, ctx: Optional[Context] = None):
+        self.vp = np.ascontiguousarray(view_projection, dtype=np.float32).reshape(16)
+        self.ctx = ctx or default_context()
+
+    @classmethod
+    def from_view_projection(cls, vp, ctx: Optional[Context] = None) -> "Frustum":
+        return cls(vp, ctx)
+
+
+def get_visible_chunks_frustum(positions, camera_position, view_projection, view_distance: int,
+                               frustum_culling: bool = True, ctx: Optional[Context] = None) -> np.ndarray:
+    """World::get_visible_chunks_frustum (world.rs:118-146) -> (N,) u8 visibility flags."""
+    ctx = ctx or default_context()
+    positions = np.ascontiguousarray(positions, dtype=np.int32).reshape(-1, 3)
+    vp = np.ascontiguousarray(view_projection, dtype=np.float32).reshape(16)
+    cam = np.ascontiguousarray(camera_position, dtype=np.float32).reshape(3)
+    out = np.zeros(positions.shape[0], dtype=np.uint8)
+    ctx.check(ctx.lib.vx_cull_chunks(ctx.handle, _p(positions), positions.shape[0], _p(vp), _p(cam), int(view_distance),
+                                     1 if frustum_culling else 0, _p(out)))
+    return out
+
+
+class Framebuffer:
+    """framebuffer.rs:197-245: ARGB colour + f32 depth, row-major."""
+
+    def __init__(self, width: int, height: int):
+        self.width = int(width)
+        self.height = int(height)
+        self.color_buffer = np.zeros((self.height, self.width), dtype=np.uint32)
+        self.depth_buffer = np.full((self.height, self.width), np.inf, dtype=np.float32)
+
+    def clear(self, clear_color: int):  # framebuffer.rs:219
+        self.color_buffer[...] = np.uint32(clear_color)
+        self.depth_buffer[...] = np.inf
+
+
+class Rasterizer:
+    """rasterizer.rs:335-431.  pub fields: backface_culling, enable_shading, shading (via frame config), atlas."""
+
+    def __init__(self, ctx: Optional[Context] = None, atlas: Optional[VxAtlas] = None):
+        self.ctx = ctx or default_context()
+        self.backface_culling = True
+        self.enable_shading = True
+        self.differential_projection = False
+        if atlas is not None:  # new_with_atlas rasterizer.rs:357
+            self.ctx.set_atlas(atlas)
+
+    def _cfg(self, w, h) -> VxFrameConfig:
+        cfg = default_frame_config(w, h)
+        cfg.backface_culling = 1 if self.backface_culling else 0
+        cfg.enable_shading = 1 if self.enable_shading else 0
+        cfg.differential_projection = 1 if self.differential_projection else 0
+        return cfg
+
+    def _render(self, batch: MeshBatch, mesh_id: int, view_proj, fb: Framebuffer, rect):
+        vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+        rect = np.ascontiguousarray(rect, dtype=np.int32)
+        cfg = self._cfg(fb.width, fb.height)
+        self.ctx.check(self.ctx.lib.vx_render_mesh(self.ctx.handle, batch.handle, int(mesh_id), _p(vp), C.byref(cfg), _p(rect),
+                                                   _p(fb.color_buffer), _p(fb.depth_buffer)))
+
+    def render_mesh(self, batch: MeshBatch, mesh_id: int, view_proj, framebuffer: Framebuffer):
+        """rasterizer.rs:385: whole framebuffer (one stripe)."""
+        self._render(batch, mesh_id, view_proj, framebuffer, (0, 0, framebuffer.width, framebuffer.height))
+
+    def render_mesh_into_slice(self, batch: MeshBatch, mesh_id: int, view_proj, framebuffer: Framebuffer, y0: int, rows: int):
+        """rasterizer.rs:413: FrameSlice = rows [y0, y0+rows) of the framebuffer."""
+        self._render(batch, mesh_id, view_proj, framebuffer, (0, y0, framebuffer.width, rows))
+
+    def render_mesh_into_tile(self, batch: MeshBatch, mesh_id: int, view_proj, framebuffer: Framebuffer, x0, y0, tw, th):
+        """rasterizer.rs:423: FrameTile rectangle."""
+        self._render(batch, mesh_id, view_proj, framebuffer, (x0, y0, tw, th))
+
+
+def render_frame(batch: MeshBatch, view_proj, camera_position, cfg: VxFrameConfig, mesh_ids=None, view_distance: int = 0,
+                 color_out=None, depth_out=None, want_depth: bool = True, ctx: Optional[Context] = None):
+    """main.rs:379-608 (+ :283-297, :368-377).  Returns (color (rows,W) u32, depth (rows,W) f32 or None, survivors i32)."""
+    ctx = ctx or batch.ctx
+    vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+    cam = np.ascontiguousarray(camera_position, dtype=np.float32).reshape(3)
+    rows = cfg.stripe_rows if cfg.stripe_rows > 0 else cfg.height
+    if color_out is None:
+        color_out = np.empty((rows, cfg.width), dtype=np.uint32)
+    if depth_out is None and want_depth:
+        depth_out = np.empty((rows, cfg.width), dtype=np.float32)
+    if mesh_ids is not None:
+        mesh_ids = np.ascontiguousarray(mesh_ids, dtype=np.int32)
+        n = int(mesh_ids.shape[0])
+        cap = max(1, n)
+    else:
+        n = -1
+        cap = max(1, batch.info().n_chunks)
+    surv = np.zeros(cap, dtype=np.int32)
+    ns = C.c_int32(0)
+    ctx.check(ctx.lib.vx_render_frame(ctx.handle, batch.handle, _p(mesh_ids), n, _p(vp), _p(cam), int(view_distance), C.byref(cfg),
+                                      _p(color_out), _p(depth_out), _p(surv), C.byref(ns)))
+    return color_out, depth_out, surv[:ns.value].copy()
+
+
+def render_frame_device(batch: MeshBatch, view_proj, camera_position, cfg: VxFrameConfig, view_distance: int,
+                        ctx: Optional[Context] = None):
+    """Device-resident frame: filter A on the device over the batch's chunks, nothing copied back."""
+    ctx = ctx or batch.ctx
+    vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+    cam = np.ascontiguousarray(camera_position, dtype=np.float32).reshape(3)
+    ctx.check(ctx.lib.vx_render_frame_device(ctx.handle, batch.handle, None, -1, _p(vp), _p(cam), int(view_distance), C.byref(cfg)))
+
+
+def frame_stats(ctx: Context) -> VxFrameStats:
+    st = VxFrameStats()
+    ctx.check(ctx.lib.vx_frame_stats(ctx.handle, C.byref(st)))
+    return st
+
+
+def framebuffer_device(ctx: Context):
+    dc, dd, rows, width = C.c_void_p(), C.c_void_p(), C.c_int32(), C.c_int32()
+    ctx.check(ctx.lib.vx_framebuffer_device(ctx.handle, C.byref(dc), C.byref(dd), C.byref(rows), C.byref(width)))
+    return dc.value, dd.value, rows.value, width.value
+
+
+class FaceBasis:
+    """differential_projection.rs:18-82: origin, tangent, bitangent, normal in clip space."""
+
+    def __init__(self, m: np.ndarray):
+        self.origin, self.tangent, self.bitangent, self.normal = m[0], m[1], m[2], m[3]
+        self.matrix = m
+
+    @classmethod
+    def from_face_direction(cls, face_dir: int, chunk_pos, slice_idx: int, view_proj, ctx: Optional[Context] = None) -> "FaceBasis":
+        return face_bases([face_dir], [chunk_pos], [slice_idx], view_proj, ctx)[0]
+
+    def is_front_facing(self) -> bool:  # differential_projection.rs:78-82
+        return bool(self.normal[2] < 0.0)
+
+    def project_packet_bounds(self, u_min, v_min, u_len, v_len, ctx: Optional[Context] = None):
+        """project_packet_bounds_simd / project_single_scalar (:92-196) -> x_min, y_min, x_max, y_max, depth_near (NDC)."""
+        ctx = ctx or default_context()
+        arrs = [np.ascontiguousarray(a, dtype=np.uint8) for a in (u_min, v_min, u_len, v_len)]
+        n = int(arrs[0].shape[0])
+        outs = [np.zeros(n, dtype=np.float32) for _ in range(5)]
+        basis = np.ascontiguousarray(self.matrix, dtype=np.float32)
+        ctx.check(ctx.lib.vx_project_packet(ctx.handle, _p(basis), *[_p(a) for a in arrs], n, *[_p(o) for o in outs]))
+        return outs
+
+
+def face_bases(faces: Sequence[int], chunk_pos, slice_idx, view_proj, ctx: Optional[Context] = None):
+    ctx = ctx or default_context()
+    faces = np.ascontiguousarray(faces, dtype=np.int32)
+    n = int(faces.shape[0])
+    cp = np.ascontiguousarray(chunk_pos, dtype=np.int32).reshape(n, 3)
+    sl = np.ascontiguousarray(slice_idx, dtype=np.uint8).reshape(n)
+    vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+    out = np.zeros((n, 4, 4), dtype=np.float32)
+    ctx.check(ctx.lib.vx_face_basis(ctx.handle, _p(faces), _p(cp), _p(sl), n, _p(vp), _p(out)))
+    return [FaceBasis(out[i]) for i in range(n)]
+
+
+def decompress_and_transform_vertices(vertices, chunk_offset, view_proj, ctx: Optional[Context] = None) -> np.ndarray:
+    """simd_vertex.rs:24: (n,8) u8 Vertex records -> (n,4) clip-space f32."""
+    ctx = ctx or default_context()
+    v = np.ascontiguousarray(vertices, dtype=np.uint8).reshape(-1, 8)
+    off = np.ascontiguousarray(chunk_offset, dtype=np.float32).reshape(3)
+    vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+    out = np.zeros((v.shape[0], 4), dtype=np.float32)
+    ctx.check(ctx.lib.vx_transform_vertices(ctx.handle, _p(v), v.shape[0], _p(off), _p(vp), _p(out)))
+    return out
+
+
+def project_mesh_vertices(batch: MeshBatch, mesh_id: int, view_proj, differential: bool, ctx: Optional[Context] = None) -> np.ndarray:
+    """Clip-space corners (n_quads,4,4) of a mesh's quads as the raster setup computes them (rasterizer.rs:1092-1185)."""
+    ctx = ctx or batch.ctx
+    h = batch._host or batch.download()
+    n = int(h["quad_count"][mesh_id])
+    out = np.zeros((max(n, 1), 4, 4), dtype=np.float32)
+    vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+    ctx.check(ctx.lib.vx_project_mesh_vertices(ctx.handle, batch.handle, int(mesh_id), _p(vp), 1 if differential else 0, _p(out), C.c_int64(max(n, 1))))
+    return out[:n]

@@ -1,0 +1,108 @@
+// vx_common.cuh -- shared host-side plumbing for libvx_b200.so (context, device buffers, error handling).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/vx_b200.h"
+
+#define VX_NUM_SMS_B200 148
+
+struct VxDeviceBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    // grow-only device allocation; contents are NOT preserved on growth
+    cudaError_t reserve(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+        size_t want = need + need / 4 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+struct VxPinnedBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMallocHost(&ptr, need + need / 4 + 256);
+        if (e == cudaSuccess) bytes = need + need / 4 + 256;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+struct VxMeshBatch {
+    int32_t n_chunks = 0;
+    int64_t cap_quads = 0;   // capacity of d_quads in quads
+    int64_t total_quads = -1; // -1 until read back
+    int32_t n_meshes = -1;
+    VxDeviceBuffer quads, quad_base, quad_count, slice_offsets, face_aabb, has_mesh, positions;
+    VxDeviceBuffer cursor; // 2 x unsigned long long: quad cursor, mesh counter
+};
+
+struct VxFrameScratch;
+
+struct VxContext {
+    int device = 0;
+    int num_sms = VX_NUM_SMS_B200;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    std::string last_error;
+    VxAtlas atlas;
+    bool atlas_dirty = true;
+    VxFrameScratch *frame = nullptr; // owned by vx_frame.cu
+    // small reusable staging buffers
+    VxDeviceBuffer tmp_a, tmp_b, tmp_c, tmp_d;
+    VxPinnedBuffer pinned;
+};
+
+inline int vx_fail(VxContext *ctx, int code, const char *msg) {
+    if (ctx) ctx->last_error = msg ? msg : "";
+    return code;
+}
+
+inline int vx_cuda_fail(VxContext *ctx, cudaError_t e, const char *what, const char *file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+    if (ctx) ctx->last_error = buf;
+    return e == cudaErrorMemoryAllocation ? VX_ERR_OOM : VX_ERR_CUDA;
+}
+
+#define VX_CUDA(ctx, expr)                                                        \
+    do {                                                                          \
+        cudaError_t _e = (expr);                                                  \
+        if (_e != cudaSuccess) return vx_cuda_fail((ctx), _e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define VX_CHECK_LAUNCH(ctx)                                                      \
+    do {                                                                          \
+        (ctx)->launches++;                                                        \
+        cudaError_t _e = cudaGetLastError();                                      \
+        if (_e != cudaSuccess) return vx_cuda_fail((ctx), _e, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+// frame scratch lifetime hooks implemented in vx_frame.cu
+void vx_frame_scratch_destroy(VxContext *ctx);

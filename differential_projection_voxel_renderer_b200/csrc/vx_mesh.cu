@@ -1,0 +1,606 @@
+// vx_mesh.cu -- binary greedy meshing of 32^3 chunks on sm_100a.
+//
+// Reference semantics: /root/reference/src/meshing/binary_greedy.rs:83-121 (mesh_chunk_in_world),
+// :213-264 (mesh_face), :286-440 (generate_binary_masks), :683-807 (greedy_mesh_slice_into) and
+// mesh.rs:283-307 (TinyQuad::new), :369-397 (FaceList::add_quad), :489-523 (ChunkMesh::add_quad).
+//
+// Design (one CTA per chunk, persistent over the batch):
+//   stage 1  every thread streams 32-voxel x-rows with two 128-bit loads and SWAR-packs the two
+//            block-type bits of each voxel into two 32-bit words (bits along x) -> 2 x 32 x 32
+//            word bit-planes in shared memory (8 KB instead of the 32 KB byte volume).  Neighbour
+//            chunks contribute six 32x32-bit solid halo planes.
+//   stage 2  face exposure is pure word logic on the planes (A_t & ~S_neighbour; +-X by a 1-bit
+//            shift with the halo bit inserted).  A warp owns one (face, slice) unit: it brings the
+//            exposure mask into the reference orientation (lane = row, bit = column) with a 5-step
+//            shuffle bit-matrix transpose, then runs the greedy merge with the row words in
+//            registers: the run is found with ffs, the row extension with ONE __ballot_sync over
+//            all rows below + ffs, the consumed bits are cleared lane-parallel.
+//   output   quads are emitted in exact reference order (face, slice, block type, row, column).
+//            Pass 1 counts per (face, slice), a CTA scan gives the slice offsets, one atomicAdd
+//            reserves the chunk's range in the batch quad stream, pass 2 re-runs the (cheap) merge
+//            and writes the 3-byte TinyQuads at their final position.
+#include "vx_common.cuh"
+
+namespace {
+
+constexpr int MESH_THREADS = 256;
+constexpr int MESH_WARPS = MESH_THREADS / 32;
+constexpr int PS = 33; // padded row stride of the 32x32 word planes (bank-conflict free both ways)
+constexpr unsigned FULL = 0xffffffffu;
+
+struct MeshSmem {
+    uint32_t P0[32 * PS];        // [y*PS + z], bit x = block_type bit 0
+    uint32_t P1[32 * PS];        // [y*PS + z], bit x = block_type bit 1
+    uint32_t MX[2][3][32 * PS];  // [sign][type-1][x*PS + y], bit z : +-X exposure in greedy orientation
+    uint32_t halo[6][32];        // neighbour solid planes, see load_halos()
+    uint32_t cnt[192];           // quads per (face, slice)
+    uint32_t offs[192];          // exclusive offsets inside the chunk
+    uint32_t faceTot[6], faceBase[6];
+    uint32_t faceRows[6], faceCols[6], faceSlices[6];
+    uint32_t base, total, overflow;
+};
+
+// 4 voxels (one per byte, values 0..3) -> 4 bits, voxel k -> bit k.  bit = 0 or 1 selects the type bit.
+__device__ __forceinline__ uint32_t gather4(uint32_t w, int bit) {
+    return (((w >> bit) & 0x01010101u) * 0x01020408u) >> 24;
+}
+
+__device__ __forceinline__ void pack_row(const uint4 a, const uint4 b, uint32_t &p0, uint32_t &p1) {
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    p0 = 0;
+    p1 = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        p0 |= gather4(w[j], 0) << (4 * j);
+        p1 |= gather4(w[j], 1) << (4 * j);
+    }
+}
+
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// 32x32 bit-matrix transpose across a warp: in: lane i holds row i (bit j = column j);
+// out: lane j holds column j (bit i = row i).
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const uint32_t m = s == 16 ? 0x0000ffffu : s == 8 ? 0x00ff00ffu : s == 4 ? 0x0f0f0f0fu : s == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(FULL, x, s);
+        x = (lane & s) ? ((x & ~m) | ((y >> s) & m)) : ((x & m) | ((y << s) & ~m));
+    }
+    return x;
+}
+
+// Greedy merge of one 32x32 mask (binary_greedy.rs:683-807).  Lane = row, d = that row's bits.
+// EMIT=false: returns the quad count.  EMIT=true: writes TinyQuads (mesh.rs:283-307) of block type
+// `type` to out[3*(pos + k)]; if out4 != nullptr writes VxQuad {row, col, width, height} instead.
+template <bool EMIT>
+__device__ __forceinline__ uint32_t greedy_warp(uint32_t d, int lane, uint32_t type, uint8_t *out, uint32_t pos,
+                                                VxQuad *out4) {
+    uint32_t n = 0;
+    uint32_t rows = __ballot_sync(FULL, d != 0);
+    while (rows) {
+        const int r = __ffs(rows) - 1;
+        rows &= rows - 1;
+        uint32_t cur = __shfl_sync(FULL, d, r);
+        while (cur) {
+            const int col = __ffs(cur) - 1;
+            const uint32_t run = ~(cur >> col);
+            const int h = run ? (__ffs(run) - 1) : 32; // trailing_ones
+            const uint32_t hmask = h >= 32 ? FULL : ((1u << h) - 1u);
+            const uint32_t m = hmask << col;
+            // rows below that still hold the whole run
+            const uint32_t ok = __ballot_sync(FULL, lane > r && (d & m) == m);
+            const uint32_t below = r == 31 ? 0u : (ok >> (r + 1));
+            const int ext = __ffs(~below) - 1; // consecutive rows r+1.. (bits >= 31-r are 0 -> terminates)
+            if (lane > r && lane <= r + ext) d &= ~m;
+            if (EMIT) {
+                const uint32_t w = 1u + (uint32_t)ext;
+                if (out4) {
+                    if (lane == 0) out4[pos + n] = VxQuad{(uint8_t)r, (uint8_t)col, (uint8_t)w, (uint8_t)h};
+                } else {
+                    const uint32_t b0 = (uint32_t)r | (((uint32_t)col & 7u) << 5);
+                    const uint32_t b1 = ((uint32_t)col >> 3) | ((w - 1u) << 2);
+                    const uint32_t b2 = ((uint32_t)h - 1u) | (type << 6);
+                    const uint32_t packed = b0 | (b1 << 8) | (b2 << 16);
+                    if (lane < 3) out[3 * (size_t)(pos + n) + lane] = (uint8_t)(packed >> (8 * lane));
+                }
+            }
+            n++;
+            cur &= ~m;
+        }
+    }
+    return n;
+}
+
+struct ChunkArgs {
+    const uint8_t *voxels;
+    const int32_t *neighbors;
+    const uint8_t *uniform_flags;
+    int32_t n_chunks;
+    uint8_t *quads;
+    unsigned long long cap_quads;
+    uint32_t *quad_base, *quad_count, *slice_offsets;
+    int32_t *face_aabb;
+    uint8_t *has_mesh;
+    unsigned long long *cursor; // [0] quad cursor, [1] mesh counter, [2] overflow flag
+};
+
+// halo[f][i]: f=0/1 (+X/-X): i = y, bit z;  f=2/3 (+Y/-Y): i = z, bit x;  f=4/5 (+Z/-Z): i = y, bit x.
+__device__ void load_halos(MeshSmem &sm, const ChunkArgs &a, int chunk, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    // resolve the six neighbours (warp-uniform values, computed redundantly)
+    const uint8_t *nbp[6];
+    uint32_t fill[6];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        const int32_t nb = a.neighbors ? a.neighbors[(size_t)chunk * 6 + f] : VX_NBR_NONE;
+        nbp[f] = nullptr;
+        fill[f] = 0;
+        if (nb >= 0 && nb < a.n_chunks) {
+            const uint8_t uf = a.uniform_flags ? a.uniform_flags[nb] : 0;
+            if (uf) fill[f] = (uf - 1) != 0 ? FULL : 0u; // Uniform neighbour: is_solid (binary_greedy.rs:305-313)
+            else nbp[f] = a.voxels + (size_t)nb * VX_CHUNK_VOLUME;
+        } else if (nb == VX_NBR_UNIFORM_SOLID) fill[f] = FULL;
+    }
+    // +-X: one byte per (y,z): warp task (f, y), lane = z, ballot -> word with bit z
+    for (int t = warp; t < 64; t += MESH_WARPS) {
+        const int f = t >> 5, y = t & 31;
+        uint32_t word = fill[f];
+        if (nbp[f]) {
+            const uint8_t v = nbp[f][lane * 1024 + y * 32 + (f == 0 ? 0 : 31)];
+            word = __ballot_sync(FULL, v != 0);
+        }
+        if (lane == 0) sm.halo[f][y] = word;
+    }
+    // +-Y, +-Z: one 32-byte x-row per entry, SWAR packed: thread task (f, i)
+    if (tid < 128) {
+        const int f = 2 + (tid >> 5), i = tid & 31;
+        uint32_t word = fill[f];
+        if (nbp[f]) {
+            size_t off;
+            if (f == 2) off = (size_t)i * 1024;                 // +Y neighbour: row y=0 of plane z=i
+            else if (f == 3) off = (size_t)i * 1024 + 31 * 32;  // -Y neighbour: row y=31
+            else if (f == 4) off = (size_t)i * 32;              // +Z neighbour: plane z=0, row y=i
+            else off = (size_t)31 * 1024 + (size_t)i * 32;      // -Z neighbour: plane z=31
+            const uint4 *p = reinterpret_cast<const uint4 *>(nbp[f] + off);
+            uint32_t p0, p1;
+            pack_row(__ldg(p), __ldg(p + 1), p0, p1);
+            word = p0 | p1;
+        }
+        sm.halo[f][i] = word;
+    }
+}
+
+// exposure words (bits x) of the three block types for voxel row (y,z) against neighbour solid word nbS
+__device__ __forceinline__ void exposure(uint32_t a0, uint32_t a1, uint32_t nbS, uint32_t e[3]) {
+    const uint32_t open = ~nbS;
+    e[0] = a0 & ~a1 & open; // Grass = 1
+    e[1] = a1 & ~a0 & open; // Dirt  = 2
+    e[2] = a0 & a1 & open;  // Stone = 3
+}
+
+// Row words (lane = row, bits = column) of unit (face, slice) for the three block types.
+// axis 1 (Y): rows x, cols z   axis 2 (Z): rows x, cols y   (binary_greedy.rs:446-458); axis 0 comes from MX.
+__device__ __forceinline__ void unit_rows_yz(const MeshSmem &sm, int face, int slice, int lane, uint32_t d[3]) {
+    const int axis = face >> 1;
+    const bool positive = (face & 1) == 0;
+    uint32_t a0, a1, nbS;
+    if (axis == 1) { // lane = z
+        a0 = sm.P0[slice * PS + lane];
+        a1 = sm.P1[slice * PS + lane];
+        const int ny = positive ? slice + 1 : slice - 1;
+        if (ny >= 0 && ny < 32) nbS = sm.P0[ny * PS + lane] | sm.P1[ny * PS + lane];
+        else nbS = sm.halo[face][lane];
+    } else { // axis 2, lane = y
+        a0 = sm.P0[lane * PS + slice];
+        a1 = sm.P1[lane * PS + slice];
+        const int nz = positive ? slice + 1 : slice - 1;
+        if (nz >= 0 && nz < 32) nbS = sm.P0[lane * PS + nz] | sm.P1[lane * PS + nz];
+        else nbS = sm.halo[face][lane];
+    }
+    uint32_t e[3];
+    exposure(a0, a1, nbS, e);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) d[t] = __any_sync(FULL, e[t] != 0) ? transpose32(e[t], lane) : 0u;
+}
+
+template <bool EMIT>
+__device__ __forceinline__ void process_units(MeshSmem &sm, const ChunkArgs &a, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int unit = warp; unit < 192; unit += MESH_WARPS) {
+        const int face = unit >> 5, slice = unit & 31;
+        uint32_t d[3];
+        if (face < 2) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) d[t] = sm.MX[face][t][slice * PS + lane];
+        } else {
+            unit_rows_yz(sm, face, slice, lane, d);
+        }
+        if (!EMIT) {
+            uint32_t n = 0, rowsAny = 0, colsAny = 0;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const uint32_t any = __ballot_sync(FULL, d[t] != 0);
+                if (any) {
+                    rowsAny |= any;
+                    colsAny |= __reduce_or_sync(FULL, d[t]);
+                    n += greedy_warp<false>(d[t], lane, 0, nullptr, 0, nullptr);
+                }
+            }
+            if (lane == 0) {
+                sm.cnt[unit] = n;
+                if (n) {
+                    atomicOr(&sm.faceRows[face], rowsAny);
+                    atomicOr(&sm.faceCols[face], colsAny);
+                    atomicOr(&sm.faceSlices[face], 1u << slice);
+                }
+            }
+        } else {
+            if (sm.cnt[unit] == 0) continue;
+            uint32_t pos = sm.base + sm.offs[unit];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                if (__any_sync(FULL, d[t] != 0)) pos += greedy_warp<true>(d[t], lane, (uint32_t)(t + 1), a.quads, pos, nullptr);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(MESH_THREADS) mesh_chunks_kernel(ChunkArgs a) {
+    __shared__ MeshSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int chunk = blockIdx.x; chunk < a.n_chunks; chunk += gridDim.x) {
+        uint32_t *so = a.slice_offsets + (size_t)chunk * 198;
+        int32_t *ab = a.face_aabb + (size_t)chunk * 36;
+        if (a.uniform_flags && a.uniform_flags[chunk]) { // Uniform chunk -> None (binary_greedy.rs:87)
+            for (int i = tid; i < 198; i += MESH_THREADS) so[i] = 0;
+            if (tid < 36) ab[tid] = (tid % 6) < 3 ? 32 : 0;
+            if (tid == 0) {
+                a.quad_base[chunk] = 0;
+                a.quad_count[chunk] = 0;
+                a.has_mesh[chunk] = 0;
+            }
+            continue;
+        }
+        // ---- stage 1: byte volume -> bit planes
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.voxels + (size_t)chunk * VX_CHUNK_VOLUME);
+        uint4 ra[4], rb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { // issue all loads first (8 x 128-bit in flight per thread)
+            const int r = tid + k * MESH_THREADS;
+            ra[k] = ld_stream(src + 2 * r);
+            rb[k] = ld_stream(src + 2 * r + 1);
+        }
+        if (tid < 18) (&sm.faceRows[0])[tid] = 0; // faceRows, faceCols, faceSlices are contiguous
+        load_halos(sm, a, chunk, tid);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = tid + k * MESH_THREADS; // r = z*32 + y
+            uint32_t p0, p1;
+            pack_row(ra[k], rb[k], p0, p1);
+            const int y = r & 31, z = r >> 5;
+            sm.P0[y * PS + z] = p0;
+            sm.P1[y * PS + z] = p1;
+        }
+        __syncthreads();
+
+        // ---- stage 2a: +-X exposure, transposed into MX[sign][type][x][y] (bits z)
+        for (int item = warp; item < 64; item += MESH_WARPS) {
+            const int sign = item >> 5, y = item & 31; // lane = z
+            const uint32_t a0 = sm.P0[y * PS + lane], a1 = sm.P1[y * PS + lane];
+            const uint32_t S = a0 | a1;
+            const uint32_t hb = (sm.halo[sign][y] >> lane) & 1u;
+            const uint32_t nbS = sign == 0 ? ((S >> 1) | (hb << 31)) : ((S << 1) | hb);
+            uint32_t e[3];
+            exposure(a0, a1, nbS, e);
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const uint32_t col = __any_sync(FULL, e[t] != 0) ? transpose32(e[t], lane) : 0u; // lane = x, bits z
+                sm.MX[sign][t][lane * PS + y] = col;
+            }
+        }
+        __syncthreads();
+
+        // ---- pass 1: count
+        process_units<false>(sm, a, tid);
+        __syncthreads();
+        if (tid < 6) {
+            uint32_t run = 0;
+            for (int s = 0; s < 32; ++s) {
+                sm.offs[tid * 32 + s] = run;
+                run += sm.cnt[tid * 32 + s];
+            }
+            sm.faceTot[tid] = run;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t run = 0;
+            for (int f = 0; f < 6; ++f) {
+                sm.faceBase[f] = run;
+                run += sm.faceTot[f];
+            }
+            sm.total = run;
+            unsigned long long base = 0;
+            if (run) {
+                base = atomicAdd(a.cursor, (unsigned long long)run);
+                atomicAdd(a.cursor + 1, 1ull);
+            }
+            sm.overflow = (base + run > a.cap_quads) ? 1u : 0u;
+            if (sm.overflow) atomicExch(a.cursor + 2, 1ull);
+            sm.base = (uint32_t)base;
+            a.quad_base[chunk] = (uint32_t)base;
+            a.quad_count[chunk] = run;
+            a.has_mesh[chunk] = run ? 1 : 0; // mesh.is_empty() -> None (binary_greedy.rs:116-120)
+        }
+        __syncthreads();
+        if (tid < 192) {
+            const int f = tid >> 5;
+            const uint32_t o = sm.offs[tid] + sm.faceBase[f];
+            sm.offs[tid] = o;
+            so[f * 33 + (tid & 31)] = o;
+        }
+        if (tid < 6) so[tid * 33 + 32] = sm.faceBase[tid] + sm.faceTot[tid];
+        if (tid < 6) { // FaceList::min / max (mesh.rs:369-397) from the occupancy of the exposure masks
+            const uint32_t rows = sm.faceRows[tid], cols = sm.faceCols[tid], sl = sm.faceSlices[tid];
+            int mn[3] = {32, 32, 32}, mx[3] = {0, 0, 0};
+            if (sl) {
+                const int axis = tid >> 1, add = (tid & 1) ? 0 : 1; // axis_pos = slice + 1 for positive faces
+                const int s0 = __ffs(sl) - 1 + add, s1 = 31 - __clz(sl) + add;
+                const int u0 = __ffs(rows) - 1, u1 = 32 - __clz(rows);
+                const int v0 = __ffs(cols) - 1, v1 = 32 - __clz(cols);
+                if (axis == 0) { mn[0] = s0; mx[0] = s1; mn[1] = u0; mx[1] = u1; mn[2] = v0; mx[2] = v1; }
+                else if (axis == 1) { mn[0] = u0; mx[0] = u1; mn[1] = s0; mx[1] = s1; mn[2] = v0; mx[2] = v1; }
+                else { mn[0] = u0; mx[0] = u1; mn[1] = v0; mx[1] = v1; mn[2] = s0; mx[2] = s1; }
+            }
+            for (int k = 0; k < 3; ++k) {
+                ab[tid * 6 + k] = mn[k];
+                ab[tid * 6 + 3 + k] = mx[k];
+            }
+        }
+        __syncthreads();
+        // ---- pass 2: emit
+        if (sm.total && !sm.overflow) process_units<true>(sm, a, tid);
+        __syncthreads();
+    }
+}
+
+// KAT surface: one warp per 32-row mask.
+__global__ void greedy_slices_kernel(const uint32_t *masks, int n, VxQuad *out, int32_t *n_out) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n) return;
+    const uint32_t d = masks[(size_t)w * 32 + lane];
+    const uint32_t c = greedy_warp<true>(d, lane, 0, nullptr, 0, out + (size_t)w * 512);
+    if (lane == 0) n_out[w] = (int32_t)c;
+}
+
+int batch_alloc(VxContext *ctx, VxMeshBatch *b, int32_t n, int64_t cap_quads) {
+    b->n_chunks = n;
+    VX_CUDA(ctx, b->quad_base.reserve(sizeof(uint32_t) * (size_t)n));
+    VX_CUDA(ctx, b->quad_count.reserve(sizeof(uint32_t) * (size_t)n));
+    VX_CUDA(ctx, b->slice_offsets.reserve(sizeof(uint32_t) * 198 * (size_t)n));
+    VX_CUDA(ctx, b->face_aabb.reserve(sizeof(int32_t) * 36 * (size_t)n));
+    VX_CUDA(ctx, b->has_mesh.reserve((size_t)n));
+    VX_CUDA(ctx, b->positions.reserve(sizeof(int32_t) * 3 * (size_t)n));
+    VX_CUDA(ctx, b->cursor.reserve(sizeof(unsigned long long) * 4));
+    VX_CUDA(ctx, b->quads.reserve(3 * (size_t)cap_quads + 16));
+    b->cap_quads = cap_quads;
+    return VX_OK;
+}
+
+int run_mesher(VxContext *ctx, const uint8_t *d_vox, const int32_t *d_nb, const uint8_t *d_uf, VxMeshBatch *b,
+               bool allow_regrow) {
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        VX_CUDA(ctx, cudaMemsetAsync(b->cursor.ptr, 0, sizeof(unsigned long long) * 4, ctx->stream));
+        ChunkArgs a;
+        a.voxels = d_vox;
+        a.neighbors = d_nb;
+        a.uniform_flags = d_uf;
+        a.n_chunks = b->n_chunks;
+        a.quads = b->quads.as<uint8_t>();
+        a.cap_quads = (unsigned long long)b->cap_quads;
+        a.quad_base = b->quad_base.as<uint32_t>();
+        a.quad_count = b->quad_count.as<uint32_t>();
+        a.slice_offsets = b->slice_offsets.as<uint32_t>();
+        a.face_aabb = b->face_aabb.as<int32_t>();
+        a.has_mesh = b->has_mesh.as<uint8_t>();
+        a.cursor = b->cursor.as<unsigned long long>();
+        int per_sm = 0;
+        VX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mesh_chunks_kernel, MESH_THREADS, 0));
+        if (per_sm < 1) per_sm = 1;
+        int grid = ctx->num_sms * per_sm;
+        if (grid > b->n_chunks) grid = b->n_chunks;
+        mesh_chunks_kernel<<<grid, MESH_THREADS, 0, ctx->stream>>>(a);
+        VX_CHECK_LAUNCH(ctx);
+        b->total_quads = -1;
+        b->n_meshes = -1;
+        if (!allow_regrow) return VX_OK;
+        unsigned long long h[4];
+        VX_CUDA(ctx, cudaMemcpyAsync(h, b->cursor.ptr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!h[2]) {
+            b->total_quads = (int64_t)h[0];
+            b->n_meshes = (int32_t)h[1];
+            return VX_OK;
+        }
+        if (h[0] >= (1ull << 32)) return vx_fail(ctx, VX_ERR_CAPACITY, "more than 2^32 quads in one batch");
+        // quad stream was too small: grow to the exact need and re-run
+        VX_CUDA(ctx, b->quads.reserve(3 * (size_t)h[0] + 16));
+        b->cap_quads = (int64_t)h[0];
+    }
+    return vx_fail(ctx, VX_ERR_CAPACITY, "mesher output did not fit after regrow");
+}
+
+} // namespace
+
+extern "C" {
+
+int vx_mesh_chunks_device(VxContext *ctx, const uint8_t *d_voxels, const int32_t *d_positions,
+                          const int32_t *d_neighbors, const uint8_t *d_uniform_flags, int32_t n_chunks,
+                          VxMeshBatch **out) {
+    if (!ctx || !out || n_chunks < 0 || (n_chunks > 0 && !d_voxels)) return vx_fail(ctx, VX_ERR_INVALID, "vx_mesh_chunks_device: bad argument");
+    if ((reinterpret_cast<uintptr_t>(d_voxels) & 15) != 0) return vx_fail(ctx, VX_ERR_INVALID, "voxels must be 16-byte aligned");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    VxMeshBatch *b = new VxMeshBatch();
+    // typical terrain chunk: ~200 quads (binary_greedy.rs:91); start with 512 per chunk, regrow on demand
+    int rc = batch_alloc(ctx, b, n_chunks, (int64_t)(n_chunks > 0 ? n_chunks : 1) * 512);
+    if (rc == VX_OK && n_chunks > 0) {
+        if (d_positions) {
+            cudaError_t e = cudaMemcpyAsync(b->positions.ptr, d_positions, sizeof(int32_t) * 3 * (size_t)n_chunks,
+                                            cudaMemcpyDeviceToDevice, ctx->stream);
+            if (e != cudaSuccess) rc = vx_cuda_fail(ctx, e, "copy positions", __FILE__, __LINE__);
+        } else {
+            cudaMemsetAsync(b->positions.ptr, 0, sizeof(int32_t) * 3 * (size_t)n_chunks, ctx->stream);
+        }
+    }
+    if (rc == VX_OK && n_chunks > 0) rc = run_mesher(ctx, d_voxels, d_neighbors, d_uniform_flags, b, true);
+    if (rc == VX_OK && n_chunks == 0) { b->total_quads = 0; b->n_meshes = 0; }
+    if (rc != VX_OK) {
+        vx_mesh_batch_release(ctx, b);
+        return rc;
+    }
+    *out = b;
+    return VX_OK;
+}
+
+int vx_remesh_chunks_device(VxContext *ctx, const uint8_t *d_voxels, const int32_t *d_neighbors,
+                            const uint8_t *d_uniform_flags, VxMeshBatch *batch) {
+    if (!ctx || !batch || !d_voxels) return vx_fail(ctx, VX_ERR_INVALID, "vx_remesh_chunks_device: bad argument");
+    if (batch->n_chunks == 0) return VX_OK;
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    return run_mesher(ctx, d_voxels, d_neighbors, d_uniform_flags, batch, false);
+}
+
+int vx_mesh_chunks(VxContext *ctx, const uint8_t *voxels, const int32_t *positions, const int32_t *neighbors,
+                   const uint8_t *uniform_flags, int32_t n_chunks, VxMeshBatch **out) {
+    if (!ctx || !out || n_chunks < 0 || (n_chunks > 0 && !voxels)) return vx_fail(ctx, VX_ERR_INVALID, "vx_mesh_chunks: bad argument");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)n_chunks;
+    VX_CUDA(ctx, ctx->tmp_a.reserve(n * VX_CHUNK_VOLUME + 16));
+    VX_CUDA(ctx, ctx->tmp_b.reserve(n * 6 * sizeof(int32_t) + 16));
+    VX_CUDA(ctx, ctx->tmp_c.reserve(n + 16));
+    VX_CUDA(ctx, ctx->tmp_d.reserve(n * 3 * sizeof(int32_t) + 16));
+    if (n) VX_CUDA(ctx, cudaMemcpyAsync(ctx->tmp_a.ptr, voxels, n * VX_CHUNK_VOLUME, cudaMemcpyHostToDevice, ctx->stream));
+    if (n && neighbors) VX_CUDA(ctx, cudaMemcpyAsync(ctx->tmp_b.ptr, neighbors, n * 6 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (n && uniform_flags) VX_CUDA(ctx, cudaMemcpyAsync(ctx->tmp_c.ptr, uniform_flags, n, cudaMemcpyHostToDevice, ctx->stream));
+    if (n && positions) VX_CUDA(ctx, cudaMemcpyAsync(ctx->tmp_d.ptr, positions, n * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    return vx_mesh_chunks_device(ctx, ctx->tmp_a.as<uint8_t>(), positions ? ctx->tmp_d.as<int32_t>() : nullptr,
+                                 neighbors ? ctx->tmp_b.as<int32_t>() : nullptr,
+                                 uniform_flags ? ctx->tmp_c.as<uint8_t>() : nullptr, n_chunks, out);
+}
+
+int vx_mesh_batch_info(VxContext *ctx, const VxMeshBatch *b, VxMeshBatchInfo *info) {
+    if (!ctx || !b || !info) return vx_fail(ctx, VX_ERR_INVALID, "vx_mesh_batch_info: bad argument");
+    VxMeshBatch *mb = const_cast<VxMeshBatch *>(b);
+    if (mb->total_quads < 0) {
+        unsigned long long h[4];
+        VX_CUDA(ctx, cudaMemcpyAsync(h, mb->cursor.ptr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h[2]) return vx_fail(ctx, VX_ERR_CAPACITY, "remesh overflowed the batch quad stream");
+        mb->total_quads = (int64_t)h[0];
+        mb->n_meshes = (int32_t)h[1];
+    }
+    info->n_chunks = b->n_chunks;
+    info->n_meshes = mb->n_meshes;
+    info->total_quads = mb->total_quads;
+    return VX_OK;
+}
+
+int vx_mesh_batch_device(const VxMeshBatch *b, VxMeshBatchDevice *out) {
+    if (!b || !out) return VX_ERR_INVALID;
+    out->d_quads = b->quads.as<uint8_t>();
+    out->d_quad_base = b->quad_base.as<uint32_t>();
+    out->d_quad_count = b->quad_count.as<uint32_t>();
+    out->d_slice_offsets = b->slice_offsets.as<uint32_t>();
+    out->d_face_aabb = b->face_aabb.as<int32_t>();
+    out->d_has_mesh = b->has_mesh.as<uint8_t>();
+    out->d_positions = b->positions.as<int32_t>();
+    return VX_OK;
+}
+
+int vx_mesh_batch_download(VxContext *ctx, const VxMeshBatch *b, uint8_t *quads, uint32_t *quad_base,
+                           uint32_t *quad_count, uint32_t *slice_offsets, int32_t *face_aabb, uint8_t *has_mesh) {
+    if (!ctx || !b) return vx_fail(ctx, VX_ERR_INVALID, "vx_mesh_batch_download: bad argument");
+    VxMeshBatchInfo info;
+    int rc = vx_mesh_batch_info(ctx, b, &info);
+    if (rc != VX_OK) return rc;
+    const size_t n = (size_t)b->n_chunks;
+    if (quads && info.total_quads) VX_CUDA(ctx, cudaMemcpyAsync(quads, b->quads.ptr, 3 * (size_t)info.total_quads, cudaMemcpyDeviceToHost, ctx->stream));
+    if (quad_base && n) VX_CUDA(ctx, cudaMemcpyAsync(quad_base, b->quad_base.ptr, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (quad_count && n) VX_CUDA(ctx, cudaMemcpyAsync(quad_count, b->quad_count.ptr, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (slice_offsets && n) VX_CUDA(ctx, cudaMemcpyAsync(slice_offsets, b->slice_offsets.ptr, 4 * 198 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (face_aabb && n) VX_CUDA(ctx, cudaMemcpyAsync(face_aabb, b->face_aabb.ptr, 4 * 36 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (has_mesh && n) VX_CUDA(ctx, cudaMemcpyAsync(has_mesh, b->has_mesh.ptr, n, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+int vx_mesh_batch_upload(VxContext *ctx, const uint8_t *quads, int64_t total_quads, const uint32_t *quad_base,
+                         const uint32_t *quad_count, const uint32_t *slice_offsets, const int32_t *face_aabb,
+                         const uint8_t *has_mesh, const int32_t *positions, int32_t n_chunks, VxMeshBatch **out) {
+    if (!ctx || !out || n_chunks < 0 || total_quads < 0) return vx_fail(ctx, VX_ERR_INVALID, "vx_mesh_batch_upload: bad argument");
+    if (n_chunks > 0 && (!quad_base || !quad_count || !slice_offsets || !face_aabb || !has_mesh || !positions))
+        return vx_fail(ctx, VX_ERR_INVALID, "vx_mesh_batch_upload: null array");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    VxMeshBatch *b = new VxMeshBatch();
+    int rc = batch_alloc(ctx, b, n_chunks, total_quads > 0 ? total_quads : 1);
+    if (rc != VX_OK) { vx_mesh_batch_release(ctx, b); return rc; }
+    const size_t n = (size_t)n_chunks;
+    cudaError_t e = cudaSuccess;
+    auto up = [&](void *dst, const void *src, size_t bytes) {
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    };
+    up(b->quads.ptr, quads, 3 * (size_t)total_quads);
+    up(b->quad_base.ptr, quad_base, 4 * n);
+    up(b->quad_count.ptr, quad_count, 4 * n);
+    up(b->slice_offsets.ptr, slice_offsets, 4 * 198 * n);
+    up(b->face_aabb.ptr, face_aabb, 4 * 36 * n);
+    up(b->has_mesh.ptr, has_mesh, n);
+    up(b->positions.ptr, positions, 12 * n);
+    int32_t nm = 0;
+    for (size_t i = 0; i < n; ++i) nm += has_mesh[i] ? 1 : 0;
+    unsigned long long h[4] = {(unsigned long long)total_quads, (unsigned long long)nm, 0, 0};
+    up(b->cursor.ptr, h, sizeof(h));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { vx_mesh_batch_release(ctx, b); return vx_cuda_fail(ctx, e, "upload", __FILE__, __LINE__); }
+    b->total_quads = total_quads;
+    b->n_meshes = nm;
+    *out = b;
+    return VX_OK;
+}
+
+void vx_mesh_batch_release(VxContext *ctx, VxMeshBatch *b) {
+    if (!b) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    b->quads.release(); b->quad_base.release(); b->quad_count.release(); b->slice_offsets.release();
+    b->face_aabb.release(); b->has_mesh.release(); b->positions.release(); b->cursor.release();
+    delete b;
+}
+
+int vx_greedy_mesh_slices(VxContext *ctx, const uint32_t *masks, int32_t n_slices, VxQuad *out, int32_t *n_out) {
+    if (!ctx || n_slices < 0 || (n_slices > 0 && (!masks || !out || !n_out))) return vx_fail(ctx, VX_ERR_INVALID, "vx_greedy_mesh_slices: bad argument");
+    if (n_slices == 0) return VX_OK;
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)n_slices;
+    VX_CUDA(ctx, ctx->tmp_a.reserve(n * 32 * sizeof(uint32_t)));
+    VX_CUDA(ctx, ctx->tmp_b.reserve(n * 512 * sizeof(VxQuad)));
+    VX_CUDA(ctx, ctx->tmp_c.reserve(n * sizeof(int32_t)));
+    VX_CUDA(ctx, cudaMemcpyAsync(ctx->tmp_a.ptr, masks, n * 32 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    const int threads = 128;
+    const int blocks = (int)((n * 32 + threads - 1) / threads);
+    greedy_slices_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->tmp_a.as<uint32_t>(), n_slices, ctx->tmp_b.as<VxQuad>(), ctx->tmp_c.as<int32_t>());
+    VX_CHECK_LAUNCH(ctx);
+    VX_CUDA(ctx, cudaMemcpyAsync(n_out, ctx->tmp_c.ptr, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(out, ctx->tmp_b.ptr, n * 512 * sizeof(VxQuad), cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,257 @@
+// vx_misc.cu -- stand-alone entry points around the frame path: chunk visibility (filter A), FaceBasis /
+// packet projection (the reference's "Hyper-Pipeline" projection stage), legacy vertex transform and a
+// vertex dump used by the parity tests.                      (compiled with -fmad=false, see vx_math.cuh)
+#include "vx_common.cuh"
+#include "vx_math.cuh"
+
+namespace {
+
+// World::get_visible_chunks_frustum world.rs:118-146
+__global__ void cull_chunks_kernel(const int32_t *positions, int32_t n, VxMat4 vp, float cx, float cy, float cz,
+                                   int32_t view_distance, int32_t frustum, uint8_t *visible) {
+    __shared__ float planes[6][4];
+    if (threadIdx.x < 6) vx_frustum_plane(vp, threadIdx.x, planes[threadIdx.x]);
+    __syncthreads();
+    const int32_t cc[3] = {vx_f2i(floorf(cx / (float)VX_CHUNK_SIZE)), vx_f2i(floorf(cy / (float)VX_CHUNK_SIZE)),
+                           vx_f2i(floorf(cz / (float)VX_CHUNK_SIZE))};
+    const float vd_sq = (float)(view_distance * view_distance);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int32_t p[3] = {positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]};
+        visible[i] = vx_chunk_visible(p, cc, vd_sq, frustum != 0, planes) ? 1 : 0;
+    }
+}
+
+// face_coordinate_system differential_projection.rs:231-290 + FaceBasis::from_face_direction :37-62.
+// Note the mirrored (bi)tangents of the negative faces: this is the reference's FaceBasis API verbatim.
+__global__ void face_basis_kernel(const int32_t *faces, const int32_t *chunk_pos, const uint8_t *slice_idx, int32_t n,
+                                  VxMat4 vp, float *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int face = faces[i];
+    const float cw[3] = {(float)chunk_pos[3 * i] * (float)VX_CHUNK_SIZE, (float)chunk_pos[3 * i + 1] * (float)VX_CHUNK_SIZE,
+                         (float)chunk_pos[3 * i + 2] * (float)VX_CHUNK_SIZE};
+    const float s = (float)slice_idx[i];
+    const int axis = face >> 1;
+    float o[3] = {cw[0] + (axis == 0 ? s : 0.0f), cw[1] + (axis == 1 ? s : 0.0f), cw[2] + (axis == 2 ? s : 0.0f)};
+    float t[3] = {0, 0, 0}, b[3] = {0, 0, 0}, nn[3] = {0, 0, 0};
+    switch (face) {
+    case 0: t[1] = 1; b[2] = 1; nn[0] = 1; break;
+    case 1: t[1] = 1; b[2] = -1; nn[0] = -1; break;
+    case 2: t[0] = 1; b[2] = 1; nn[1] = 1; break;
+    case 3: t[0] = 1; b[2] = -1; nn[1] = -1; break;
+    case 4: t[0] = 1; b[1] = 1; nn[2] = 1; break;
+    default: t[0] = -1; b[1] = 1; nn[2] = -1; break;
+    }
+    float4 *dst = reinterpret_cast<float4 *>(out + 16 * (size_t)i);
+    dst[0] = vx_mul_vec4(vp, o[0], o[1], o[2], 1.0f);
+    dst[1] = vx_mul_vec4(vp, t[0], t[1], t[2], 0.0f);
+    dst[2] = vx_mul_vec4(vp, b[0], b[1], b[2], 0.0f);
+    dst[3] = vx_mul_vec4(vp, nn[0], nn[1], nn[2], 0.0f);
+}
+
+struct Basis {
+    float v[16];
+};
+
+// project_point :69-71 (origin + u*tangent + v*bitangent, left to right) + project_single_scalar :167-196
+__global__ void project_packet_kernel(Basis bs, const uint8_t *u_min, const uint8_t *v_min, const uint8_t *u_len,
+                                      const uint8_t *v_len, int32_t n, float *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float u0 = (float)u_min[i], v0 = (float)v_min[i];
+    const float u1 = u0 + (float)u_len[i], v1 = v0 + (float)v_len[i];
+    float nd[4][3];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float u = (c & 1) ? u1 : u0, v = (c & 2) ? v1 : v0;
+        float p[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p[k] = (bs.v[k] + u * bs.v[4 + k]) + v * bs.v[8 + k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) nd[c][k] = p[k] / p[3]; // perspective_divide :412-414
+    }
+    out[0 * (size_t)n + i] = fminf(fminf(fminf(nd[0][0], nd[1][0]), nd[2][0]), nd[3][0]);
+    out[1 * (size_t)n + i] = fminf(fminf(fminf(nd[0][1], nd[1][1]), nd[2][1]), nd[3][1]);
+    out[2 * (size_t)n + i] = fmaxf(fmaxf(fmaxf(nd[0][0], nd[1][0]), nd[2][0]), nd[3][0]);
+    out[3 * (size_t)n + i] = fmaxf(fmaxf(fmaxf(nd[0][1], nd[1][1]), nd[2][1]), nd[3][1]);
+    out[4 * (size_t)n + i] = fminf(fminf(fminf(nd[0][2], nd[1][2]), nd[2][2]), nd[3][2]);
+}
+
+// decompress_and_transform_vertices_scalar simd_vertex.rs:48-58
+__global__ void transform_vertices_kernel(const VxVertex *verts, int32_t n, float ox, float oy, float oz, VxMat4 vp,
+                                          float4 *out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint2 raw = *reinterpret_cast<const uint2 *>(verts + i); // 8-byte vertex, one 64-bit load
+        const float x = (float)(raw.x & 0xFF), y = (float)((raw.x >> 8) & 0xFF), z = (float)((raw.x >> 16) & 0xFF);
+        out[i] = vx_mul_point(vp, ox + x, oy + y, oz + z);
+    }
+}
+
+// the four clip-space corners of every quad of one mesh, as the raster setup computes them
+__global__ void project_mesh_vertices_kernel(const uint8_t *quads, const uint32_t *slice_offsets, uint32_t qbase,
+                                             uint32_t qcount, float ox, float oy, float oz, VxMat4 vp, int differential,
+                                             float4 *out) {
+    __shared__ uint32_t so[198];
+    __shared__ float4 origin[3][33];
+    for (int i = threadIdx.x; i < 198; i += blockDim.x) so[i] = slice_offsets[i];
+    for (int i = threadIdx.x; i < 99; i += blockDim.x) {
+        const int axis = i / 33, s = i % 33;
+        origin[axis][s] = vx_mul_point(vp, ox + (axis == 0 ? (float)s : 0.0f), oy + (axis == 1 ? (float)s : 0.0f),
+                                       oz + (axis == 2 ? (float)s : 0.0f));
+    }
+    __syncthreads();
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < qcount; q += gridDim.x * blockDim.x) {
+        int face = 0;
+        for (int ff = 1; ff < 6; ++ff) face += (so[ff * 33] <= q) ? 1 : 0;
+        int lo = 0, hi = 31;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (so[face * 33 + mid] <= q) lo = mid; else hi = mid - 1;
+        }
+        const int axis = face >> 1, spos = (face & 1) ? lo : lo + 1;
+        const uint8_t *qp = quads + 3 * (size_t)(qbase + q);
+        const uint32_t b0 = qp[0], b1 = qp[1], b2 = qp[2];
+        const int u = b0 & 0x1F, v = ((b0 >> 5) & 7) | ((b1 & 3) << 3);
+        const int w = ((b1 >> 2) & 0x3F) + 1, h = (b2 & 0x3F) + 1;
+        for (int i = 0; i < 4; ++i) {
+            const int cu = ((kCornerU[face] >> i) & 1) ? u + w : u;
+            const int cv = ((kCornerV[face] >> i) & 1) ? v + h : v;
+            int lx, ly, lz;
+            if (axis == 0) { lx = spos; ly = cu; lz = cv; }
+            else if (axis == 1) { lx = cu; ly = spos; lz = cv; }
+            else { lx = cu; ly = cv; lz = spos; }
+            float4 p;
+            if (!differential) p = vx_mul_point(vp, ox + (float)lx, oy + (float)ly, oz + (float)lz);
+            else {
+                const float4 o = origin[axis][spos];
+                const int ta = axis == 0 ? 1 : 0, ba = axis == 2 ? 1 : 2;
+                const float fu = (float)cu, fv = (float)cv;
+                p.x = fmaf(fu, vp.m[ta * 4 + 0], fmaf(fv, vp.m[ba * 4 + 0], o.x));
+                p.y = fmaf(fu, vp.m[ta * 4 + 1], fmaf(fv, vp.m[ba * 4 + 1], o.y));
+                p.z = fmaf(fu, vp.m[ta * 4 + 2], fmaf(fv, vp.m[ba * 4 + 2], o.z));
+                p.w = fmaf(fu, vp.m[ta * 4 + 3], fmaf(fv, vp.m[ba * 4 + 3], o.w));
+            }
+            out[4 * (size_t)q + i] = p;
+        }
+    }
+}
+
+VxMat4 to_mat(const float vp[16]) {
+    VxMat4 m;
+    memcpy(m.m, vp, sizeof(float) * 16);
+    return m;
+}
+
+} // namespace
+
+extern "C" {
+
+int vx_cull_chunks(VxContext *ctx, const int32_t *positions, int32_t n, const float vp[16], const float cam_pos[3],
+                   int32_t view_distance, int32_t frustum_culling, uint8_t *visible_out) {
+    if (!ctx || n < 0 || !vp || !cam_pos || (n > 0 && (!positions || !visible_out))) return vx_fail(ctx, VX_ERR_INVALID, "vx_cull_chunks: bad argument");
+    if (n == 0) return VX_OK;
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    VX_CUDA(ctx, ctx->tmp_a.reserve(sizeof(int32_t) * 3 * (size_t)n));
+    VX_CUDA(ctx, ctx->tmp_b.reserve((size_t)n));
+    VX_CUDA(ctx, cudaMemcpyAsync(ctx->tmp_a.ptr, positions, sizeof(int32_t) * 3 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    int grid = (n + 255) / 256;
+    if (grid > ctx->num_sms * 8) grid = ctx->num_sms * 8;
+    cull_chunks_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->tmp_a.as<int32_t>(), n, to_mat(vp), cam_pos[0], cam_pos[1], cam_pos[2],
+                                                     view_distance, frustum_culling, ctx->tmp_b.as<uint8_t>());
+    VX_CHECK_LAUNCH(ctx);
+    VX_CUDA(ctx, cudaMemcpyAsync(visible_out, ctx->tmp_b.ptr, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+int vx_face_basis(VxContext *ctx, const int32_t *faces, const int32_t *chunk_pos, const uint8_t *slice_idx, int32_t n,
+                  const float vp[16], float *basis_out) {
+    if (!ctx || n < 0 || !vp || (n > 0 && (!faces || !chunk_pos || !slice_idx || !basis_out))) return vx_fail(ctx, VX_ERR_INVALID, "vx_face_basis: bad argument");
+    if (n == 0) return VX_OK;
+    for (int32_t i = 0; i < n; ++i)
+        if (faces[i] < 0 || faces[i] > 5) return vx_fail(ctx, VX_ERR_INVALID, "face index out of range");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t N = (size_t)n;
+    VX_CUDA(ctx, ctx->tmp_a.reserve(4 * N));
+    VX_CUDA(ctx, ctx->tmp_b.reserve(12 * N));
+    VX_CUDA(ctx, ctx->tmp_c.reserve(N));
+    VX_CUDA(ctx, ctx->tmp_d.reserve(64 * N));
+    VX_CUDA(ctx, cudaMemcpyAsync(ctx->tmp_a.ptr, faces, 4 * N, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(ctx->tmp_b.ptr, chunk_pos, 12 * N, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(ctx->tmp_c.ptr, slice_idx, N, cudaMemcpyHostToDevice, ctx->stream));
+    face_basis_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->tmp_a.as<int32_t>(), ctx->tmp_b.as<int32_t>(), ctx->tmp_c.as<uint8_t>(), n,
+                                                               to_mat(vp), ctx->tmp_d.as<float>());
+    VX_CHECK_LAUNCH(ctx);
+    VX_CUDA(ctx, cudaMemcpyAsync(basis_out, ctx->tmp_d.ptr, 64 * N, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+int vx_project_packet(VxContext *ctx, const float basis[16], const uint8_t *u_min, const uint8_t *v_min,
+                      const uint8_t *u_len, const uint8_t *v_len, int32_t n, float *x_min, float *y_min,
+                      float *x_max, float *y_max, float *depth_near) {
+    if (!ctx || n < 0 || !basis) return vx_fail(ctx, VX_ERR_INVALID, "vx_project_packet: bad argument");
+    if (n == 0) return VX_OK;
+    if (!u_min || !v_min || !u_len || !v_len || !x_min || !y_min || !x_max || !y_max || !depth_near) return vx_fail(ctx, VX_ERR_INVALID, "vx_project_packet: null array");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t N = (size_t)n;
+    VX_CUDA(ctx, ctx->tmp_a.reserve(4 * N));
+    VX_CUDA(ctx, ctx->tmp_b.reserve(5 * 4 * N));
+    uint8_t *d_in = ctx->tmp_a.as<uint8_t>();
+    VX_CUDA(ctx, cudaMemcpyAsync(d_in + 0 * N, u_min, N, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(d_in + 1 * N, v_min, N, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * N, u_len, N, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(d_in + 3 * N, v_len, N, cudaMemcpyHostToDevice, ctx->stream));
+    Basis bs;
+    memcpy(bs.v, basis, sizeof(bs.v));
+    project_packet_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(bs, d_in, d_in + N, d_in + 2 * N, d_in + 3 * N, n, ctx->tmp_b.as<float>());
+    VX_CHECK_LAUNCH(ctx);
+    float *outs[5] = {x_min, y_min, x_max, y_max, depth_near};
+    for (int k = 0; k < 5; ++k)
+        VX_CUDA(ctx, cudaMemcpyAsync(outs[k], ctx->tmp_b.as<float>() + k * N, 4 * N, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+int vx_transform_vertices(VxContext *ctx, const VxVertex *verts, int32_t n, const float offset[3], const float vp[16],
+                          float *out4) {
+    if (!ctx || n < 0 || !offset || !vp || (n > 0 && (!verts || !out4))) return vx_fail(ctx, VX_ERR_INVALID, "vx_transform_vertices: bad argument");
+    if (n == 0) return VX_OK;
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t N = (size_t)n;
+    VX_CUDA(ctx, ctx->tmp_a.reserve(8 * N));
+    VX_CUDA(ctx, ctx->tmp_b.reserve(16 * N));
+    VX_CUDA(ctx, cudaMemcpyAsync(ctx->tmp_a.ptr, verts, 8 * N, cudaMemcpyHostToDevice, ctx->stream));
+    int grid = (n + 255) / 256;
+    if (grid > ctx->num_sms * 8) grid = ctx->num_sms * 8;
+    transform_vertices_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->tmp_a.as<VxVertex>(), n, offset[0], offset[1], offset[2], to_mat(vp), ctx->tmp_b.as<float4>());
+    VX_CHECK_LAUNCH(ctx);
+    VX_CUDA(ctx, cudaMemcpyAsync(out4, ctx->tmp_b.ptr, 16 * N, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+int vx_project_mesh_vertices(VxContext *ctx, const VxMeshBatch *batch, int32_t mesh_id, const float vp[16],
+                             int32_t differential, float *out, int64_t cap_quads) {
+    if (!ctx || !batch || !vp || !out || mesh_id < 0 || mesh_id >= batch->n_chunks) return vx_fail(ctx, VX_ERR_INVALID, "vx_project_mesh_vertices: bad argument");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint32_t qbase = 0, qcount = 0;
+    int32_t pos[3];
+    VX_CUDA(ctx, cudaMemcpyAsync(&qbase, batch->quad_base.as<uint32_t>() + mesh_id, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(&qcount, batch->quad_count.as<uint32_t>() + mesh_id, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(pos, batch->positions.as<int32_t>() + 3 * (size_t)mesh_id, 12, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((int64_t)qcount > cap_quads) return vx_fail(ctx, VX_ERR_CAPACITY, "output too small for the mesh's quads");
+    if (qcount == 0) return VX_OK;
+    VX_CUDA(ctx, ctx->tmp_a.reserve(64 * (size_t)qcount));
+    int grid = (int)((qcount + 127) / 128);
+    project_mesh_vertices_kernel<<<grid, 128, 0, ctx->stream>>>(batch->quads.as<uint8_t>(), batch->slice_offsets.as<uint32_t>() + (size_t)mesh_id * 198,
+                                                               qbase, qcount, (float)(pos[0] * VX_CHUNK_SIZE), (float)(pos[1] * VX_CHUNK_SIZE),
+                                                               (float)(pos[2] * VX_CHUNK_SIZE), to_mat(vp), differential, ctx->tmp_a.as<float4>());
+    VX_CHECK_LAUNCH(ctx);
+    VX_CUDA(ctx, cudaMemcpyAsync(out, ctx->tmp_a.ptr, 64 * (size_t)qcount, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,235 @@
+/*
+ * vx_b200.h -- C ABI of libvx_b200.so: the B200 (sm_100a) implementation of the
+ * per-frame voxel pipeline of gatewaytofredom/differential_projection_voxel_renderer
+ * (Rust crate `voxel_engine` 0.1.0): binary greedy meshing of 32^3 chunks, chunk
+ * frustum / screen-rect culling, differential projection of the axis-aligned quad
+ * vertices and the span (scanline) rasterizer with depth buffer and 8x8
+ * micro-textured, per-face-lit shading.
+ *
+ * The reference has no FFI: its boundary is the crate's public Rust API.  Every
+ * entry point below names the Rust item it stands in for (file:line relative to
+ * /root/reference/); INTEGRATION.md shows the `extern "C"` block and the thin
+ * `impl BinaryGreedyMesher` / `impl Rasterizer` shims a maintainer adds.
+ *
+ * Conventions
+ *   - plain pointers + sizes, POD structs, no C++/torch types;
+ *   - every call returns VX_OK (0) or a negative VX_ERR_*; there is NO CPU
+ *     fallback: without a usable CUDA device the context cannot be created and
+ *     every other call fails with VX_ERR_NO_DEVICE / VX_ERR_INVALID;
+ *   - host pointers unless the name says `_device` / `d_`;
+ *   - a VxContext owns one CUDA device + stream; calls on one context are
+ *     serialised by the caller (like `&mut Rasterizer`), different contexts are
+ *     independent (one per GPU / per thread);
+ *   - matrices are 16 f32, column-major (glam `Mat4::to_cols_array`).
+ */
+#ifndef VX_B200_H
+#define VX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VX_API __attribute__((visibility("default")))
+#else
+#define VX_API
+#endif
+
+#define VX_CHUNK_SIZE 32
+#define VX_CHUNK_VOLUME 32768
+
+enum {
+    VX_OK = 0,
+    VX_ERR_INVALID = -1,   /* bad argument */
+    VX_ERR_NO_DEVICE = -2, /* no CUDA device / wrong architecture */
+    VX_ERR_CUDA = -3,      /* CUDA runtime error, see vx_last_error */
+    VX_ERR_CAPACITY = -4,  /* an internal limit was exceeded (e.g. > 2^21 visible quads) */
+    VX_ERR_OOM = -5
+};
+
+/* neighbour codes for `neighbors` (N x 6, order +X,-X,+Y,-Y,+Z,-Z = FaceDir, mesh.rs:136-143) */
+#define VX_NBR_NONE (-1)          /* no chunk: border faces exposed (binary_greedy.rs:314) */
+#define VX_NBR_UNIFORM_AIR (-2)   /* Uniform non-solid neighbour (binary_greedy.rs:305-313) */
+#define VX_NBR_UNIFORM_SOLID (-3) /* Uniform solid neighbour */
+
+typedef struct VxContext VxContext;
+typedef struct VxMeshBatch VxMeshBatch; /* device-resident meshes of a batch of chunks */
+
+/* `Quad` mesh.rs:245-250 (x = row, y = col/bit, width = rows, height = run length) */
+typedef struct { uint8_t x, y, width, height; } VxQuad;
+
+/* `Vertex` mesh.rs:46-58 (8 bytes) */
+typedef struct { uint8_t x, y, z, block_type, light, packed; uint16_t padding; } VxVertex;
+
+/* `MicroTexture` x4 = `TextureAtlas` texture.rs:5-13,56-79 */
+typedef struct {
+    uint32_t palette[4][16];
+    uint8_t indices[4][32];
+} VxAtlas;
+
+/* Per-frame configuration: Rasterizer pub fields (rasterizer.rs:335-341), ShadingConfig
+ * (shading.rs:9-31), framebuffer size and clear colour (main.rs:393). */
+typedef struct {
+    int32_t width, height;
+    uint32_t clear_color;
+    int32_t backface_culling;
+    int32_t enable_shading;
+    float light_dir[3];
+    float ambient, diffuse;
+    /* Rows [stripe_y0, stripe_y0 + stripe_rows) are rendered and returned (a FrameSlice,
+     * framebuffer.rs:16-23).  stripe_rows == 0 means the whole frame.  Screen-space
+     * mapping always uses the full `height` (PixelTarget::full_height). */
+    int32_t stripe_y0, stripe_rows;
+    /* 0: exact reference vertex arithmetic VP*(offset+local) (rasterizer.rs:1177-1185);
+     * 1: differential projection base + x*c0 + y*c1 + z*c2 (differential_projection.rs:69). */
+    int32_t differential_projection;
+    /* 1: vx_render_frame_device only enqueues the frame (no host synchronisation); scratch overflow and
+     * statistics are then reported by vx_frame_stats(). */
+    int32_t async_submit;
+    int32_t reserved[2];
+} VxFrameConfig;
+
+typedef struct {
+    int32_t n_chunks;
+    int32_t n_meshes;     /* chunks with has_mesh != 0 */
+    int64_t total_quads;
+} VxMeshBatchInfo;
+
+/* Raw device pointers of a batch (for zero-copy interop, e.g. NCCL all-gather of quad
+ * streams between ranks).  Valid until vx_mesh_batch_release. */
+typedef struct {
+    uint8_t *d_quads;          /* 3 bytes per TinyQuad (mesh.rs:273-342) */
+    uint32_t *d_quad_base;     /* [N] first quad of chunk i */
+    uint32_t *d_quad_count;    /* [N] */
+    uint32_t *d_slice_offsets; /* [N][6][33] relative to quad_base; [f][32] = end of face f */
+    int32_t *d_face_aabb;      /* [N][6][6] FaceList min.xyz,max.xyz (mesh.rs:347-397) */
+    uint8_t *d_has_mesh;       /* [N] Option<ChunkMesh>::is_some */
+    int32_t *d_positions;      /* [N][3] chunk coordinates */
+} VxMeshBatchDevice;
+
+typedef struct {
+    int32_t n_input;          /* meshes considered */
+    int32_t n_survivors;      /* after filter B */
+    int32_t n_quads;          /* quads of the survivors */
+    int32_t n_triangles;      /* triangles after near clip + backface cull */
+    int32_t n_bin_entries;    /* (triangle, stripe) pairs */
+    int32_t n_kernel_launches;
+    int32_t reserved[2];
+} VxFrameStats;
+
+/* ---- context ---------------------------------------------------------- */
+VX_API int vx_context_create(int device_id, VxContext **out);
+VX_API void vx_context_destroy(VxContext *ctx);
+VX_API const char *vx_error_string(int code);
+/* last CUDA / validation message recorded on this context (empty string if none) */
+VX_API const char *vx_last_error(const VxContext *ctx);
+VX_API int vx_device_synchronize(VxContext *ctx);
+/* CUDA stream the context launches on (cudaStream_t as void*), for event timing */
+VX_API void *vx_context_stream(VxContext *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+VX_API int64_t vx_context_launch_count(const VxContext *ctx);
+
+/* ---- meshing ---------------------------------------------------------- */
+
+/* BinaryGreedyMesher::mesh_world (binary_greedy.rs:62-78) / mesh_chunk_in_world (:83) /
+ * mesh_chunk_in_indexed_world (:127) / mesh_chunk (:55, neighbors == NULL).
+ *   voxels        N x 32768 u8, index = z*1024 + y*32 + x (chunk.rs:52), values 0..3
+ *   positions     N x 3 chunk coordinates (kept with the batch for rendering)
+ *   neighbors     N x 6: index into this batch, or VX_NBR_*; NULL = all VX_NBR_NONE
+ *   uniform_flags N: 0 = Varied, else 1 + block_type of a Uniform chunk (-> no mesh,
+ *                 binary_greedy.rs:87); NULL = all Varied.  A neighbour index that points
+ *                 at a Uniform chunk is treated by its block type (:305-313).
+ * Host -> device copy, mesh kernel; the result stays on the device. */
+VX_API int vx_mesh_chunks(VxContext *ctx, const uint8_t *voxels, const int32_t *positions, const int32_t *neighbors,
+                   const uint8_t *uniform_flags, int32_t n_chunks, VxMeshBatch **out);
+/* Same with all four arrays already resident on the context's device. */
+VX_API int vx_mesh_chunks_device(VxContext *ctx, const uint8_t *d_voxels, const int32_t *d_positions,
+                          const int32_t *d_neighbors, const uint8_t *d_uniform_flags, int32_t n_chunks,
+                          VxMeshBatch **out);
+/* Re-mesh into an existing batch of the same n_chunks (steady-state remesh sweep: no allocation). */
+VX_API int vx_remesh_chunks_device(VxContext *ctx, const uint8_t *d_voxels, const int32_t *d_neighbors,
+                            const uint8_t *d_uniform_flags, VxMeshBatch *batch);
+VX_API int vx_mesh_batch_info(VxContext *ctx, const VxMeshBatch *b, VxMeshBatchInfo *info);
+VX_API int vx_mesh_batch_device(const VxMeshBatch *b, VxMeshBatchDevice *out);
+/* Copy a batch to host arrays (any pointer may be NULL to skip it).  Sizes: quads 3*total_quads,
+ * quad_base/quad_count N, slice_offsets N*6*33, face_aabb N*36, has_mesh N. */
+VX_API int vx_mesh_batch_download(VxContext *ctx, const VxMeshBatch *b, uint8_t *quads, uint32_t *quad_base,
+                           uint32_t *quad_count, uint32_t *slice_offsets, int32_t *face_aabb, uint8_t *has_mesh);
+/* Build a device batch from host mesh arrays (meshes produced elsewhere, e.g. gathered
+ * from the other ranks of a chunk-sharded remesh). */
+VX_API int vx_mesh_batch_upload(VxContext *ctx, const uint8_t *quads, int64_t total_quads, const uint32_t *quad_base,
+                         const uint32_t *quad_count, const uint32_t *slice_offsets, const int32_t *face_aabb,
+                         const uint8_t *has_mesh, const int32_t *positions, int32_t n_chunks, VxMeshBatch **out);
+VX_API void vx_mesh_batch_release(VxContext *ctx, VxMeshBatch *b);
+
+/* BinaryGreedyMesher::greedy_mesh_slice (binary_greedy.rs:675) for n_slices masks of 32 rows.
+ * out: up to 512 quads per slice at out[i*512 ...], n_out[i] quads. */
+VX_API int vx_greedy_mesh_slices(VxContext *ctx, const uint32_t *masks, int32_t n_slices, VxQuad *out, int32_t *n_out);
+
+/* ---- culling ---------------------------------------------------------- */
+
+/* World::get_visible_chunks_frustum (world.rs:118-146) with Frustum::from_view_projection /
+ * intersects_aabb (camera/mod.rs:123-183).  visible_out[i] in {0,1}. */
+VX_API int vx_cull_chunks(VxContext *ctx, const int32_t *positions, int32_t n, const float vp[16], const float cam_pos[3],
+                   int32_t view_distance, int32_t frustum_culling, uint8_t *visible_out);
+
+/* ---- rendering -------------------------------------------------------- */
+
+VX_API void vx_default_frame_config(VxFrameConfig *cfg, int32_t width, int32_t height);
+VX_API void vx_default_atlas(VxAtlas *atlas); /* TextureAtlas::default texture.rs:60-79 */
+/* Rasterizer::new_with_atlas (rasterizer.rs:357): atlas used by later render calls. */
+VX_API int vx_set_atlas(VxContext *ctx, const VxAtlas *atlas);
+
+/* main.rs RedrawRequested steady state (:283-297, :368-377) + render_frame (:379-608), occlusion off:
+ * VisibleMesh list -> distance sort -> AABB projection / reject (filter B) -> near-depth sort ->
+ * project + clip + backface-cull every quad -> stripe-binned span rasterization -> framebuffer.
+ *   mesh_ids      chunks of `batch` that passed filter A (caller order = tie-break order), or NULL
+ *                 with n_meshes < 0 to run filter A on the device over the batch's own positions
+ *                 (view_distance then required)
+ *   color_out     rows x width u32 ARGB (may be NULL), depth_out rows x width f32 (may be NULL),
+ *                 rows = stripe_rows or height
+ *   survivors_out draw order (capacity n_meshes / n_chunks), may be NULL */
+VX_API int vx_render_frame(VxContext *ctx, const VxMeshBatch *batch, const int32_t *mesh_ids, int32_t n_meshes,
+                    const float vp[16], const float cam_pos[3], int32_t view_distance, const VxFrameConfig *cfg,
+                    uint32_t *color_out, float *depth_out, int32_t *survivors_out, int32_t *n_survivors);
+/* Device-resident variant: nothing is copied back; the frame stays in the context's framebuffer
+ * (see vx_framebuffer_device).  Used with CUDA-event timing and for multi-GPU composition. */
+VX_API int vx_render_frame_device(VxContext *ctx, const VxMeshBatch *batch, const int32_t *d_mesh_ids, int32_t n_meshes,
+                           const float vp[16], const float cam_pos[3], int32_t view_distance,
+                           const VxFrameConfig *cfg);
+/* Device pointers of the last rendered frame: colour (u32) and depth (f32), rows x width. */
+VX_API int vx_framebuffer_device(VxContext *ctx, uint32_t **d_color, float **d_depth, int32_t *rows, int32_t *width);
+VX_API int vx_frame_stats(VxContext *ctx, VxFrameStats *out);
+
+/* Rasterizer::render_mesh / render_mesh_into_slice / render_mesh_into_tile (rasterizer.rs:385-431)
+ * for one mesh into a caller framebuffer (W x H host arrays, read-modify-write: depth-tested against
+ * the existing contents).  rect = PixelTarget::rect() = (x0, y0, w, h). */
+VX_API int vx_render_mesh(VxContext *ctx, const VxMeshBatch *batch, int32_t mesh_id, const float vp[16],
+                   const VxFrameConfig *cfg, const int32_t rect[4], uint32_t *color_inout, float *depth_inout);
+
+/* ---- hyper-pipeline pieces ------------------------------------------- */
+
+/* FaceBasis::from_face_direction (differential_projection.rs:37-62) for n (face, chunk, slice) triples.
+ * basis_out: n x 16 f32 = origin, tangent, bitangent, normal. */
+VX_API int vx_face_basis(VxContext *ctx, const int32_t *faces, const int32_t *chunk_pos, const uint8_t *slice_idx, int32_t n,
+                  const float vp[16], float *basis_out);
+/* FaceBasis::project_packet_bounds_simd / project_single_scalar (differential_projection.rs:92-196) for
+ * n quads sharing one basis (SoA u8 arrays as FacePacket32, face_packets.rs:13-25), exact division.
+ * Outputs n f32 each: NDC x_min, y_min, x_max, y_max, depth_near (ProjectedPacket :295-304). */
+VX_API int vx_project_packet(VxContext *ctx, const float basis[16], const uint8_t *u_min, const uint8_t *v_min,
+                      const uint8_t *u_len, const uint8_t *v_len, int32_t n, float *x_min, float *y_min,
+                      float *x_max, float *y_max, float *depth_near);
+/* simd_vertex::decompress_and_transform_vertices (simd_vertex.rs:24): out4 = n x 4 clip-space f32. */
+VX_API int vx_transform_vertices(VxContext *ctx, const VxVertex *verts, int32_t n, const float offset[3], const float vp[16],
+                          float *out4);
+/* Clip-space corners of the quads of one mesh exactly as the raster path computes them
+ * (rasterizer.rs:1092-1185): out = n_quads x 4 x 4 f32; mode as VxFrameConfig.differential_projection. */
+VX_API int vx_project_mesh_vertices(VxContext *ctx, const VxMeshBatch *batch, int32_t mesh_id, const float vp[16],
+                             int32_t differential, float *out, int64_t cap_quads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
