@@ -1,0 +1,263 @@
+"""Pins the CPU oracle against the known-answer tests the reference's own test-suite holds for the hot
+path.  Runs on CPU."""
+import numpy as np
+import pytest
+
+import vx_kat as kat
+
+FACES = range(6)
+
+
+def mesh_one(ob, vox, nb_vox=None):
+    return ob.mesh_chunks(vox.reshape(1, -1))
+
+
+# ---- greedy slice KATs: src/meshing/binary_greedy.rs:814-855 -------------------------------------------
+def test_greedy_empty(ob):
+    assert ob.greedy_mesh_slice(np.zeros(32, np.uint32)).shape[0] == 0
+
+
+def test_greedy_single(ob):
+    m = np.zeros(32, np.uint32)
+    m[0] = 1
+    q = ob.greedy_mesh_slice(m)
+    assert q.tolist() == [[0, 0, 1, 1]]
+
+
+def test_greedy_vertical_line(ob):
+    m = np.zeros(32, np.uint32)
+    m[0] = 0b1111
+    q = ob.greedy_mesh_slice(m)
+    assert q.shape[0] == 1 and q[0, 2] == 1 and q[0, 3] == 4
+
+
+def test_greedy_rectangle(ob):
+    m = np.zeros(32, np.uint32)
+    m[:3] = 0b1111
+    q = ob.greedy_mesh_slice(m)
+    assert q.shape[0] == 1 and q[0, 2] == 3 and q[0, 3] == 4
+
+
+def test_greedy_microbench_masks(ob):  # benches/microbench.rs:21-38 workloads, answers by construction
+    masks = kat.slice_masks()
+    assert ob.greedy_mesh_slice(masks["full"]).tolist() == [[0, 0, 32, 32]]
+    q = ob.greedy_mesh_slice(masks["checker_rows"])
+    assert q.shape[0] == 16 and all(r[2] == 1 and r[3] == 32 for r in q.tolist())
+    q = ob.greedy_mesh_slice(masks["sparse"])  # two full-height columns
+    assert q.tolist() == [[0, 0, 32, 1], [0, 31, 32, 1]]
+    assert ob.greedy_mesh_slice(masks["alt_bits"]).shape[0] == 512
+
+
+def test_greedy_covers_mask_exactly(ob):
+    rng = np.random.default_rng(7)
+    for _ in range(50):
+        m = rng.integers(0, 2 ** 32, size=32, dtype=np.uint64).astype(np.uint32)
+        m &= rng.integers(0, 2 ** 32, size=32, dtype=np.uint64).astype(np.uint32)
+        q = ob.greedy_mesh_slice(m)
+        cover = np.zeros((32, 32), dtype=np.int32)
+        for r, c, w, h in q.tolist():
+            cover[r:r + w, c:c + h] += 1
+        bits = ((m[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).astype(np.int32)
+        assert np.array_equal(cover, bits)
+
+
+# ---- TinyQuad KATs: src/meshing/mesh.rs:694-728 ---------------------------------------------------------
+@pytest.mark.parametrize("u,v,w,h,bt", [(0, 0, 1, 1, 0), (31, 31, 32, 32, 3), (5, 10, 3, 7, 2), (16, 16, 16, 16, 1)])
+def test_tinyquad_roundtrip(ob, u, v, w, h, bt):
+    p = ob.tinyquad_pack(u, v, w, h, bt)
+    assert p.shape == (3,)  # size_of::<TinyQuad>() == 3
+    assert ob.unpack_quads(p).tolist() == [[u, v, w, h, bt]]
+
+
+# ---- chunk KATs: tests/meshing_tests.rs ------------------------------------------------------------------
+def test_single_voxel_six_faces(ob):  # :55-86
+    mb = mesh_one(ob, kat.chunk_single_voxel())
+    assert mb.quad_count[0] == 6 and mb.has_mesh[0] == 1
+    uq = ob.unpack_quads(mb.chunk_quads(0))
+    for f in FACES:
+        q = kat.quads_of_face(uq, mb.slice_offsets[0], f)
+        assert q.shape[0] == 1 and q[0, 2] == 1 and q[0, 3] == 1 and q[0, 4] == kat.STONE
+
+
+def test_face_positions(ob):  # :88-138  voxel at origin: faces on x/y/z = 1 (positive) or 0 (negative)
+    mb = mesh_one(ob, kat.chunk_single_voxel(0, 0, 0))
+    for f in FACES:
+        s = kat.slice_of_quad(mb.slice_offsets[0], f, 0)
+        slice_pos = s + 1 if f % 2 == 0 else s  # rasterizer.rs:896-900
+        assert slice_pos == (1 if f % 2 == 0 else 0)
+
+
+def test_top_and_bottom_face_height(ob):  # :140-191
+    mb = mesh_one(ob, kat.chunk_single_voxel(5, 10, 5, kat.GRASS))
+    assert kat.slice_of_quad(mb.slice_offsets[0], 2, 0) + 1 == 11  # +Y face plane at y = 11
+    assert kat.slice_of_quad(mb.slice_offsets[0], 3, 0) == 10      # -Y face plane at y = 10
+
+
+def test_internal_faces_culled(ob):  # :193-220
+    mb = mesh_one(ob, kat.chunk_two_adjacent())
+    assert mb.quad_count[0] == 6
+    for f in (0, 1):
+        s = kat.slice_of_quad(mb.slice_offsets[0], f, 0)
+        assert (s + 1 if f == 0 else s) != 11
+
+
+def test_2x2_merges(ob):  # :257-281
+    mb = mesh_one(ob, kat.chunk_2x2_plane())
+    uq = ob.unpack_quads(mb.chunk_quads(0))
+    top = kat.quads_of_face(uq, mb.slice_offsets[0], 2)
+    assert top.shape[0] == 1 and top[0, 2] == 2 and top[0, 3] == 2
+
+
+def test_uniform_chunks_give_no_mesh(ob):  # :284-309
+    for t in (kat.AIR, kat.STONE):
+        vox = np.full((1, 32768), t, dtype=np.uint8)
+        mb = ob.mesh_chunks(vox, None, np.array([1 + t], dtype=np.uint8))
+        assert mb.has_mesh[0] == 0 and mb.quad_count[0] == 0
+
+
+def test_types_not_merged(ob):  # :418-470
+    mb = mesh_one(ob, kat.chunk_two_types())
+    uq = ob.unpack_quads(mb.chunk_quads(0))
+    top = kat.quads_of_face(uq, mb.slice_offsets[0], 2)
+    assert top.shape[0] == 2 and sorted(top[:, 4].tolist()) == [kat.GRASS, kat.STONE]
+
+
+def test_cross_chunk_boundary_culling(ob):  # :530-625  solid voxels touching across the +X border
+    a = kat.empty_chunk(); kat.set_block(a, 31, 5, 5, kat.STONE)
+    b = kat.empty_chunk(); kat.set_block(b, 0, 5, 5, kat.STONE)
+    vox = np.stack([a.reshape(-1), b.reshape(-1)])
+    nb = np.full((2, 6), -1, dtype=np.int32)
+    nb[0, 0] = 1  # +X of chunk 0 is chunk 1
+    nb[1, 1] = 0  # -X of chunk 1 is chunk 0
+    mb = ob.mesh_chunks(vox, nb)
+    assert mb.quad_count.tolist() == [5, 5]
+    so = mb.slice_offsets
+    assert so[0, 0, 32] - so[0, 0, 0] == 0  # no +X face on chunk 0
+    assert so[1, 1, 32] - so[1, 1, 0] == 0  # no -X face on chunk 1
+    alone = ob.mesh_chunks(vox)  # without neighbour info both keep 6
+    assert alone.quad_count.tolist() == [6, 6]
+
+
+def test_uniform_solid_neighbour_hides_border(ob):  # binary_greedy.rs:305-313
+    a = kat.empty_chunk(); kat.set_block(a, 5, 31, 5, kat.STONE)
+    nb = np.full((1, 6), -1, dtype=np.int32)
+    nb[0, 2] = -3
+    assert ob.mesh_chunks(a.reshape(1, -1), nb).quad_count[0] == 5
+    nb[0, 2] = -2
+    assert ob.mesh_chunks(a.reshape(1, -1), nb).quad_count[0] == 6
+
+
+def test_dense_solid_six_big_quads(ob):  # benches/meshing.rs:28-41
+    mb = mesh_one(ob, kat.chunk_dense_solid())
+    uq = ob.unpack_quads(mb.chunk_quads(0))
+    assert uq.tolist() == [[0, 0, 32, 32, kat.STONE]] * 6
+    assert mb.face_aabb[0, 0].tolist() == [32, 0, 0, 32, 32, 32]  # +X face plane at x = 32
+    assert mb.face_aabb[0, 1].tolist() == [0, 0, 0, 0, 32, 32]
+
+
+def test_winding_matches_face_normal(ob):  # tests/meshing_tests.rs:311-373, mesh.rs:753-889
+    from differential_projection_voxel_renderer_b200 import camera
+    ident = np.eye(4, dtype=np.float32).reshape(16)
+    normals = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], dtype=np.float32)
+    for f in FACES:
+        clip = ob.quad_clip_vertices(f, 10 + (1 if f % 2 == 0 else 0), 3, 4, 2, 5, (0, 0, 0), ident)
+        p = clip[:, :3]
+        n = np.cross(p[1] - p[0], p[2] - p[0])
+        n /= np.linalg.norm(n)
+        assert float(np.dot(n, normals[f])) > 0.9
+
+
+# ---- frustum KAT: src/camera/mod.rs:186-212 --------------------------------------------------------------
+def test_frustum_culls_box_behind_camera(ob):
+    from differential_projection_voxel_renderer_b200 import camera
+    cam = camera.Camera((0, 0, 0), 16.0 / 9.0)
+    planes = ob.frustum_from_vp(cam.view_projection())
+    assert ob.frustum_intersects_aabb(planes, (-1, -1, -10), (1, 1, -8))
+    assert not ob.frustum_intersects_aabb(planes, (-1, -1, 8), (1, 1, 10))
+
+
+# ---- differential projection: tests/differential_projection_tests.rs:78-176, :436-453 ---------------------
+def test_basis_projection_matches_full_mvp(ob):
+    from differential_projection_voxel_renderer_b200 import camera
+    vp = camera.mat4_mul(camera.perspective_rh(np.radians(70.0), 16 / 9, 0.1, 1000.0),
+                         camera.look_at_rh((64, 50, 100), (64, 32, 64), (0, 1, 0))).reshape(16)
+    m = vp.reshape(4, 4)
+    rng = np.random.default_rng(3)
+    for f in FACES:
+        basis = ob.face_basis(f, (1, 0, 2), 7, vp)
+        # tangent/bitangent world directions of the reference's (mirrored) bases: differential_projection.rs:231-290
+        t = [(0, 1, 0), (0, 1, 0), (1, 0, 0), (1, 0, 0), (1, 0, 0), (-1, 0, 0)][f]
+        b = [(0, 0, 1), (0, 0, -1), (0, 0, 1), (0, 0, -1), (0, 1, 0), (0, 1, 0)][f]
+        o = np.array([32, 0, 64], dtype=np.float64)
+        o[f // 2] += 7
+        for _ in range(20):
+            u, v = float(rng.integers(0, 33)), float(rng.integers(0, 33))
+            w = o + u * np.array(t) + v * np.array(b)
+            full = m.T.astype(np.float64) @ np.array([w[0], w[1], w[2], 1.0])
+            got = ob.basis_project_point(basis, u, v)
+            assert np.allclose(got, full, atol=1e-2)  # reference tolerance :137-176
+    origin = ob.face_basis(2, (0, 0, 0), 5, vp)[0]  # slice -> origin :436-453
+    assert np.allclose(origin, m.T @ np.array([0, 5, 0, 1], dtype=np.float32), atol=1e-4)
+
+
+# ---- texture / shading constants: texture.rs:60-123, shading.rs:90-110, SURVEY 8 a16/a17 ------------------
+def test_shading_constants(ob):
+    cfg = ob.default_frame_config(64, 64)
+    fps = [int(ob.lib().vxo_face_light(__import__("ctypes").byref(cfg), f) * 256.0) for f in range(6)]
+    assert fps == [148, 89, 237, 89, 134, 89]
+    assert ob.lib().vxo_shade_color_u32(0xFFFFFFFF, 1.0) == 0xFFFFFFFF
+    assert ob.lib().vxo_shade_color_u32(0xFF808080, 0.5) == 0xFF404040
+
+
+def test_atlas_noise_texture(ob):
+    a = ob.default_atlas()
+    seed, idx = 12345, []
+    for _ in range(32):
+        seed = (seed * 1103515245 + 12345) & 0xFFFFFFFF
+        idx.append((seed >> 16) & 0xFF)
+    for t in (1, 2, 3):
+        assert list(a.indices[t]) == idx  # same LCG stream for all three noise textures
+    assert a.palette[1][0] == 0xFF007D00 and a.palette[1][1] == 0xFF005D00  # rgb565 0x03E0 / 0x02E0 expanded
+
+
+# ---- rasterizer pixel-centre rule: tests/rasterizer_{gap,x_gap}_test.rs -----------------------------------
+def _one_quad_batch(ob, vox):
+    return ob.mesh_chunks(vox.reshape(1, -1))
+
+
+def test_span_renderer_draws_single_voxel(ob):  # tests/rendering_pipeline_tests.rs:17-73 (320x180, > 0 px)
+    from differential_projection_voxel_renderer_b200 import camera
+    mb = _one_quad_batch(ob, kat.chunk_single_voxel(16, 16, 16))
+    cam = camera.Camera((16.5, 16.5, 30.0), 320 / 180)
+    cfg = ob.default_frame_config(320, 180)
+    color = np.full((180, 320), cfg.clear_color, dtype=np.uint32)
+    depth = np.full((180, 320), np.inf, dtype=np.float32)
+    ob.render_mesh(mb, 0, cam.view_projection(), cfg, ob.default_atlas(), (0, 0, 320, 180), color, depth)
+    assert int((color != cfg.clear_color).sum()) > 0
+    assert np.isfinite(depth[color != cfg.clear_color]).all()
+
+
+def test_stripes_leave_no_gaps(ob):  # tests/rasterizer_slice_gap_test.rs:1-79: stripe union == full-frame render
+    from differential_projection_voxel_renderer_b200 import camera
+    mb = _one_quad_batch(ob, kat.chunk_slab())
+    cam = camera.Camera((16, 40, 80), 256 / 192)
+    cfg = ob.default_frame_config(256, 192)
+    atlas = ob.default_atlas()
+    full_c = np.full((192, 256), cfg.clear_color, dtype=np.uint32); full_d = np.full((192, 256), np.inf, dtype=np.float32)
+    ob.render_mesh(mb, 0, cam.view_projection(), cfg, atlas, (0, 0, 256, 192), full_c, full_d)
+    st_c = np.full((192, 256), cfg.clear_color, dtype=np.uint32); st_d = np.full((192, 256), np.inf, dtype=np.float32)
+    for y0 in range(0, 192, 7):
+        ob.render_mesh(mb, 0, cam.view_projection(), cfg, atlas, (0, y0, 256, min(7, 192 - y0)), st_c, st_d)
+    assert np.array_equal(full_c, st_c) and np.array_equal(full_d.view(np.uint32), st_d.view(np.uint32))
+    assert int((full_c != cfg.clear_color).sum()) > 1000  # near slab covers a large area (:314-360)
+
+
+def test_near_plane_clip(ob):  # src/rendering/rasterizer.rs:166-247: camera inside the slab still draws, no NaN depth
+    from differential_projection_voxel_renderer_b200 import camera
+    mb = _one_quad_batch(ob, kat.chunk_slab())
+    cam = camera.Camera((16, 12.5, 16), 320 / 180)
+    cfg = ob.default_frame_config(320, 180)
+    color = np.full((180, 320), cfg.clear_color, dtype=np.uint32); depth = np.full((180, 320), np.inf, dtype=np.float32)
+    ob.render_mesh(mb, 0, cam.view_projection(), cfg, ob.default_atlas(), (0, 0, 320, 180), color, depth)
+    assert int((color != cfg.clear_color).sum()) > 0
+    assert not np.isnan(depth).any()
