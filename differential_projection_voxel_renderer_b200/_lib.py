@@ -40,7 +40,7 @@ class VxFrameConfig(C.Structure):
                 ("light_dir", C.c_float * 3), ("ambient", C.c_float), ("diffuse", C.c_float),
                 ("stripe_y0", C.c_int32), ("stripe_rows", C.c_int32),
                 ("differential_projection", C.c_int32), ("async_submit", C.c_int32),
-                ("reserved", C.c_int32 * 2)]
+                ("profile_kernels", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class VxMeshBatchInfo(C.Structure):
@@ -87,6 +87,7 @@ PROTOTYPES = {
     "vx_render_frame_device": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig)]),
     "vx_framebuffer_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I), C.POINTER(_I)]),
     "vx_frame_stats": (C.c_int, [_P, C.POINTER(VxFrameStats)]),
+    "vx_frame_kernel_times": (C.c_int, [_P, _P]),
     "vx_render_mesh": (C.c_int, [_P, _P, _I, _P, C.POINTER(VxFrameConfig), _P, _P, _P]),
     "vx_face_basis": (C.c_int, [_P, _P, _P, _P, _I, _P, _P]),
     "vx_project_packet": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),

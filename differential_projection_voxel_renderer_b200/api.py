@@ -381,6 +381,13 @@ def frame_stats(ctx: Context) -> VxFrameStats:
     return st
 
 
+def frame_kernel_times(ctx: Context) -> np.ndarray:
+    """ms of [cull+sort, setup, bin fill, raster] for the last frame rendered with cfg.profile_kernels = 1."""
+    out = np.zeros(4, dtype=np.float32)
+    ctx.check(ctx.lib.vx_frame_kernel_times(ctx.handle, _p(out)))
+    return out
+
+
 def framebuffer_device(ctx: Context):
     dc, dd, rows, width = C.c_void_p(), C.c_void_p(), C.c_int32(), C.c_int32()
     ctx.check(ctx.lib.vx_framebuffer_device(ctx.handle, C.byref(dc), C.byref(dd), C.byref(rows), C.byref(width)))

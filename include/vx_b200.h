@@ -88,7 +88,10 @@ typedef struct {
     /* 1: vx_render_frame_device only enqueues the frame (no host synchronisation); scratch overflow and
      * statistics are then reported by vx_frame_stats(). */
     int32_t async_submit;
-    int32_t reserved[2];
+    /* 1: bracket each of the four frame kernels with CUDA events on the context's stream
+     * (cull+sort, setup, bin fill, raster); read the durations with vx_frame_kernel_times(). */
+    int32_t profile_kernels;
+    int32_t reserved[1];
 } VxFrameConfig;
 
 typedef struct {
@@ -202,6 +205,9 @@ VX_API int vx_render_frame_device(VxContext *ctx, const VxMeshBatch *batch, cons
 /* Device pointers of the last rendered frame: colour (u32) and depth (f32), rows x width. */
 VX_API int vx_framebuffer_device(VxContext *ctx, uint32_t **d_color, float **d_depth, int32_t *rows, int32_t *width);
 VX_API int vx_frame_stats(VxContext *ctx, VxFrameStats *out);
+/* CUDA-event durations (ms) of the last frame rendered with profile_kernels = 1:
+ * [0] cull + draw order, [1] project/clip/setup, [2] stripe-bin fill, [3] span raster + write-out. */
+VX_API int vx_frame_kernel_times(VxContext *ctx, float ms_out[4]);
 
 /* Rasterizer::render_mesh / render_mesh_into_slice / render_mesh_into_tile (rasterizer.rs:385-431)
  * for one mesh into a caller framebuffer (W x H host arrays, read-modify-write: depth-tested against

@@ -1,0 +1,28 @@
+"""Short program for ncu: one world remesh (818 chunks) + a few 1280x720 vd12 frames.  Not a benchmark."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import vx_scenes  # noqa: E402
+from differential_projection_voxel_renderer_b200 import api  # noqa: E402
+
+frames = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+pos, world, p, v, nb = vx_scenes.terrain_scene(12)
+cam = vx_scenes.main_camera(1280, 720)
+ctx = api.Context(0)
+batch = api.BinaryGreedyMesher.mesh_batch(v, p, nb, None, ctx)
+print("quads", batch.info().total_quads)
+cfg = api.default_frame_config(1280, 720)
+for _ in range(frames):
+    api.render_frame_device(batch, cam.view_projection(), cam.position, cfg, 12, ctx)
+ctx.synchronize()
+st = api.frame_stats(ctx)
+print("survivors", st.n_survivors, "tris", st.n_triangles, "entries", st.n_bin_entries)
+batch.release()
+ctx.close()
