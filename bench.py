@@ -245,6 +245,7 @@ def run_cuda(args):
                 dist.gather(my_stripe, gather_bufs, dst=0)  # composite: disjoint stripes into GPU0
 
     # ---- warm-up + correctness guard ----------------------------------------------------------------------------
+    api.render_frame_device(batch, vp, cam.position, cfg, VD, ctx)  # one synchronous frame sizes the frame scratch
     for _ in range(max(3, args.warmup)):
         step_device()
     ctx.synchronize()
@@ -313,7 +314,7 @@ def run_cuda(args):
         api.render_frame_device(batch, vp, cam.position, cfg_prof, VD, ctx)
         ksum += api.frame_kernel_times(ctx)
     kms = ksum / nprof
-    knames = ["frame_cull_sort_kernel", "frame_setup_kernel", "frame_fill_kernel", "frame_raster_kernel"]
+    knames = ["frame_cull_sort_kernel", "frame_setup_kernel", "(removed: bin fill fused into setup)", "frame_raster_kernel"]
     top = int(np.argmax(kms))
     st = api.frame_stats(ctx)
 

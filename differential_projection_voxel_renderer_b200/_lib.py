@@ -88,6 +88,7 @@ PROTOTYPES = {
     "vx_framebuffer_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I), C.POINTER(_I)]),
     "vx_frame_stats": (C.c_int, [_P, C.POINTER(VxFrameStats)]),
     "vx_frame_kernel_times": (C.c_int, [_P, _P]),
+    "vx_frame_bin_counts": (C.c_int, [_P, _P, _I, C.POINTER(_I), C.POINTER(_I)]),
     "vx_render_mesh": (C.c_int, [_P, _P, _I, _P, C.POINTER(VxFrameConfig), _P, _P, _P]),
     "vx_face_basis": (C.c_int, [_P, _P, _P, _P, _I, _P, _P]),
     "vx_project_packet": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),

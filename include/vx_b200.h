@@ -208,6 +208,8 @@ VX_API int vx_frame_stats(VxContext *ctx, VxFrameStats *out);
 /* CUDA-event durations (ms) of the last frame rendered with profile_kernels = 1:
  * [0] cull + draw order, [1] project/clip/setup, [2] stripe-bin fill, [3] span raster + write-out. */
 VX_API int vx_frame_kernel_times(VxContext *ctx, float ms_out[4]);
+/* Diagnostics: triangles binned per 128x8 tile in the last frame (row-major tile grid, ntx x nty). */
+VX_API int vx_frame_bin_counts(VxContext *ctx, uint32_t *counts_out, int32_t cap, int32_t *ntx, int32_t *nty);
 
 /* Rasterizer::render_mesh / render_mesh_into_slice / render_mesh_into_tile (rasterizer.rs:385-431)
  * for one mesh into a caller framebuffer (W x H host arrays, read-modify-write: depth-tested against

@@ -23,6 +23,12 @@ for _ in range(frames):
     api.render_frame_device(batch, cam.view_projection(), cam.position, cfg, 12, ctx)
 ctx.synchronize()
 st = api.frame_stats(ctx)
-print("survivors", st.n_survivors, "tris", st.n_triangles, "entries", st.n_bin_entries)
+print("survivors", st.n_survivors, "tris", st.n_triangles, "entries", st.n_bin_entries, "max_bin", st.reserved[0])
+bc = api.frame_bin_counts(ctx)
+np.set_printoptions(linewidth=250)
+print("tile grid", bc.shape, "rows: max per tile row")
+print(bc.max(axis=1))
+print("per tile-row sum", bc.sum(axis=1))
+print("hist", np.histogram(bc, bins=[0, 1, 8, 64, 256, 1024, 4096, 16384, 1 << 20])[0])
 batch.release()
 ctx.close()
