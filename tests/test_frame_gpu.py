@@ -150,6 +150,36 @@ def test_render_mesh_slice_and_tile_targets(ctx, ob):
     batch.release()
 
 
+def test_render_mesh_equal_depth_keeps_the_first(ctx, ob):
+    """framebuffer.rs:45 is a strict `depth < stored`: re-drawing identical geometry (here the same slab with another
+    block type) must not replace a single pixel, on the read-modify-write path as in the reference."""
+    slab = kat.chunk_slab().reshape(1, -1)
+    other = slab.copy()
+    other[other != 0] = 1 if int(slab.max()) != 1 else 3
+    vox = np.concatenate([slab, other])
+    pos = [(0, 0, 0), (0, 0, 0)]
+    batch = api.BinaryGreedyMesher.mesh_batch(vox, pos, None, None, ctx)
+    ref = ob.mesh_chunks(vox, None, None, np.asarray(pos, np.int32))
+    w, h = 256, 192
+    cam = camera.Camera((16, 40, 80), w / h)
+    vp = cam.view_projection()
+    ocfg, atlas = ob.default_frame_config(w, h), ob.default_atlas()
+    r = api.Rasterizer(ctx)
+    fb = api.Framebuffer(w, h)
+    fb.clear(0xFF87CEEB)
+    oc, od = fb.color_buffer.copy(), fb.depth_buffer.copy()
+    for mesh_id in (0, 1):
+        ob.render_mesh(ref, mesh_id, vp, ocfg, atlas, (0, 0, w, h), oc, od)
+        r.render_mesh(batch, mesh_id, vp, fb)
+        assert np.array_equal(fb.depth_buffer.view(np.uint32), od.view(np.uint32))
+        assert np.array_equal(fb.color_buffer, oc)
+    first = api.Framebuffer(w, h)
+    first.clear(0xFF87CEEB)
+    r.render_mesh(batch, 0, vp, first)
+    assert np.array_equal(first.color_buffer, fb.color_buffer), "second draw of equal depth replaced pixels"
+    batch.release()
+
+
 def test_rasterizer_flags(ctx, ob, scene5):
     _, p, batch, ref = scene5
     w, h = 320, 180
