@@ -314,7 +314,7 @@ def run_cuda(args):
         api.render_frame_device(batch, vp, cam.position, cfg_prof, VD, ctx)
         ksum += api.frame_kernel_times(ctx)
     kms = ksum / nprof
-    knames = ["frame_cull_sort_kernel", "frame_setup_kernel", "(removed: bin fill fused into setup)", "frame_raster_kernel"]
+    knames = ["frame_cull_kernel", "frame_setup_kernel", "(removed: bin fill fused into setup)", "frame_raster_kernel"]
     top = int(np.argmax(kms))
     st = api.frame_stats(ctx)
 

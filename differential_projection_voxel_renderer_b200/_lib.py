@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvx_b200.so")
+# VX_B200_LIB: development override (kernel tuning variants); the product always loads the in-tree library
+LIB_PATH = os.environ.get("VX_B200_LIB") or os.path.join(_HERE, "libvx_b200.so")
 
 VX_OK = 0
 VX_ERR_INVALID = -1
@@ -88,11 +89,14 @@ PROTOTYPES = {
     "vx_framebuffer_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I), C.POINTER(_I)]),
     "vx_frame_stats": (C.c_int, [_P, C.POINTER(VxFrameStats)]),
     "vx_frame_kernel_times": (C.c_int, [_P, _P]),
+    "vx_frame_trace": (C.c_int, [_P, _P, _I, C.POINTER(_I)]),
+    "vx_frame_setup_trace": (C.c_int, [_P, _P, _I, C.POINTER(_I)]),
     "vx_frame_bin_counts": (C.c_int, [_P, _P, _I, C.POINTER(_I), C.POINTER(_I)]),
     "vx_render_mesh": (C.c_int, [_P, _P, _I, _P, C.POINTER(VxFrameConfig), _P, _P, _P]),
     "vx_face_basis": (C.c_int, [_P, _P, _P, _P, _I, _P, _P]),
     "vx_project_packet": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "vx_transform_vertices": (C.c_int, [_P, _P, _I, _P, _P, _P]),
+    "vx_selftest_division": (C.c_int, [_P, C.c_uint64, C.c_uint64, _I, _P]),
     "vx_project_mesh_vertices": (C.c_int, [_P, _P, _I, _P, _I, _P, C.c_int64]),
 }
 

@@ -73,9 +73,11 @@ VX_HD float vx_accum_jump(float z, float s, uint32_t n) {
         const int32_t d = (int32_t)(b3 - b2); // settled lattice increment (raw bits grow with magnitude)
         if (d == 0) return z3;                // s no longer moves z: the chain is constant from here on
         const uint32_t frac = b3 & 0x7FFFFFu;
-        uint32_t kmax;
-        if (d > 0) kmax = (0x7FFFFFu - frac) / (uint32_t)d;
-        else kmax = frac >= 1u ? (frac - 1u) / (uint32_t)(-d) : 0u;
+        const uint32_t room = d > 0 ? 0x7FFFFFu - frac : (frac >= 1u ? frac - 1u : 0u);
+        const uint32_t ad = d > 0 ? (uint32_t)d : (uint32_t)(-d);
+        // common case: all n remaining steps stay inside the binade (no division needed)
+        if ((unsigned long long)n * ad <= (unsigned long long)room) return vx_u2f(b3 + (uint32_t)((int32_t)n * d));
+        const uint32_t kmax = room / ad;
         const uint32_t k = n < kmax ? n : kmax;
         z = vx_u2f(b3 + (uint32_t)((int32_t)k * d));
         n -= k;

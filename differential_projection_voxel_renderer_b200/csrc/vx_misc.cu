@@ -142,9 +142,54 @@ VxMat4 to_mat(const float vp[16]) {
     return m;
 }
 
+// vx_div_fast vs the `/` operator on pseudo-random operand pairs.  counters: [0] mismatching quotients among pairs the
+// guard accepted, [1] pairs the guard sent to the fallback, [2] pairs tested.
+__global__ void selftest_division_kernel(unsigned long long seed, unsigned long long n, int mode, unsigned long long *counters) {
+    unsigned long long bad = 0, fb = 0, cnt = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        unsigned long long x = (i + 1) * 0x9E3779B97F4A7C15ull ^ seed; // splitmix64
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        x ^= x >> 31;
+        uint32_t ua = (uint32_t)x, ub = (uint32_t)(x >> 32);
+        if (mode == 1) { // magnitudes of the raster path: exponents within +-40 of 1.0, numerator sometimes 0
+            ua = (ua & 0x807FFFFFu) | ((87u + (ua >> 23) % 80u) << 23);
+            ub = (ub & 0x807FFFFFu) | ((87u + (ub >> 23) % 80u) << 23);
+            if ((x & 0xFF000000000000ull) == 0) ua &= 0x80000000u;
+        } else if (mode == 2) { // few mantissa bits: exact and tie-prone quotients
+            ua = (ua & 0xFFF80000u);
+            ub = (ub & 0xFFF80000u);
+        }
+        const float a = __uint_as_float(ua), b = __uint_as_float(ub);
+        bool ok = true;
+        const float q = vx_div_fast(a, b, ok);
+        const float ref = a / b;
+        cnt++;
+        if (!ok) fb++;
+        else if (__float_as_uint(q) != __float_as_uint(ref) && !(q == 0.0f && ref == 0.0f)) bad++;
+    }
+    atomicAdd(&counters[0], bad);
+    atomicAdd(&counters[1], fb);
+    atomicAdd(&counters[2], cnt);
+}
+
 } // namespace
 
 extern "C" {
+
+int vx_selftest_division(VxContext *ctx, uint64_t seed, uint64_t n_pairs, int32_t mode, uint64_t counters_out[3]) {
+    if (!ctx || !counters_out) return vx_fail(ctx, VX_ERR_INVALID, "vx_selftest_division: bad argument");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    VX_CUDA(ctx, ctx->tmp_a.reserve(3 * sizeof(unsigned long long)));
+    VX_CUDA(ctx, cudaMemsetAsync(ctx->tmp_a.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    selftest_division_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(seed, n_pairs, mode, ctx->tmp_a.as<unsigned long long>());
+    VX_CHECK_LAUNCH(ctx);
+    VX_CUDA(ctx, cudaMemcpyAsync(counters_out, ctx->tmp_a.ptr, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
 
 int vx_cull_chunks(VxContext *ctx, const int32_t *positions, int32_t n, const float vp[16], const float cam_pos[3],
                    int32_t view_distance, int32_t frustum_culling, uint8_t *visible_out) {

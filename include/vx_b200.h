@@ -88,8 +88,9 @@ typedef struct {
     /* 1: vx_render_frame_device only enqueues the frame (no host synchronisation); scratch overflow and
      * statistics are then reported by vx_frame_stats(). */
     int32_t async_submit;
-    /* 1: bracket each of the four frame kernels with CUDA events on the context's stream
-     * (cull+sort, setup, bin fill, raster); read the durations with vx_frame_kernel_times(). */
+    /* 1: bracket each frame kernel with CUDA events on the context's stream (cull, setup, raster); read the
+     * durations with vx_frame_kernel_times().  2: additionally record the raster work-item timeline
+     * (vx_frame_trace). */
     int32_t profile_kernels;
     int32_t reserved[1];
 } VxFrameConfig;
@@ -208,6 +209,14 @@ VX_API int vx_frame_stats(VxContext *ctx, VxFrameStats *out);
 /* CUDA-event durations (ms) of the last frame rendered with profile_kernels = 1:
  * [0] cull + draw order, [1] project/clip/setup, [2] stripe-bin fill, [3] span raster + write-out. */
 VX_API int vx_frame_kernel_times(VxContext *ctx, float ms_out[4]);
+/* Diagnostics: timeline of the raster work items of the last frame rendered with profile_kernels = 2.
+ * out: 14 x u64 per item = tile, part | parts << 16, start ns, end ns (%globaltimer), SM id, source entries,
+ * keys-ready ns, first-expansion ns, first-task-round ns, then for thread 0's first task the clock cycles spent on
+ * record load, edge setup, span setup + jump, pixel walk, and its pixel count. */
+VX_API int vx_frame_trace(VxContext *ctx, uint64_t *out, int32_t cap_items, int32_t *n_items);
+/* Same for the setup kernel: 8 x u64 per CTA = start, ranked, projected, binned, done (ns), plan start, plan end (last
+ * CTA only), units processed.  CTAs that had no unit stay all-zero. */
+VX_API int vx_frame_setup_trace(VxContext *ctx, uint64_t *out, int32_t cap_ctas, int32_t *n_ctas);
 /* Diagnostics: triangles binned per 128x8 tile in the last frame (row-major tile grid, ntx x nty). */
 VX_API int vx_frame_bin_counts(VxContext *ctx, uint32_t *counts_out, int32_t cap, int32_t *ntx, int32_t *nty);
 
@@ -236,6 +245,14 @@ VX_API int vx_transform_vertices(VxContext *ctx, const VxVertex *verts, int32_t 
  * (rasterizer.rs:1092-1185): out = n_quads x 4 x 4 f32; mode as VxFrameConfig.differential_projection. */
 VX_API int vx_project_mesh_vertices(VxContext *ctx, const VxMeshBatch *batch, int32_t mesh_id, const float vp[16],
                              int32_t differential, float *out, int64_t cap_quads);
+
+/* ---- self tests ------------------------------------------------------- */
+
+/* The raster kernels divide with an inlined, branch-free copy of nvcc's IEEE division fast path behind an explicit
+ * exponent guard (vx_math.cuh: vx_div_fast).  This runs it against the `/` operator on n_pairs pseudo-random operand
+ * pairs (mode 0: any bit patterns, 1: magnitudes of the raster path, 2: short mantissas) and returns
+ * counters_out = {mismatches among guard-accepted pairs (must be 0), pairs sent to the fallback, pairs tested}. */
+VX_API int vx_selftest_division(VxContext *ctx, uint64_t seed, uint64_t n_pairs, int32_t mode, uint64_t counters_out[3]);
 
 #ifdef __cplusplus
 }

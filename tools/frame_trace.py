@@ -1,0 +1,73 @@
+"""Raster work-item timeline of one 1280x720 vd12 frame (diagnostics; not a benchmark):
+   python tools/frame_trace.py [W H VD]"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import vx_scenes  # noqa: E402
+from differential_projection_voxel_renderer_b200 import api  # noqa: E402
+
+W = int(sys.argv[1]) if len(sys.argv) > 1 else 1280
+H = int(sys.argv[2]) if len(sys.argv) > 2 else 720
+VD = int(sys.argv[3]) if len(sys.argv) > 3 else 12
+pos, world, p, v, nb = vx_scenes.terrain_scene(VD)
+cam = vx_scenes.main_camera(W, H)
+ctx = api.Context(0)
+batch = api.BinaryGreedyMesher.mesh_batch(v, p, nb, None, ctx)
+cfg = api.default_frame_config(W, H)
+for _ in range(3):
+    api.render_frame_device(batch, cam.view_projection(), cam.position, cfg, VD, ctx)
+cfg.profile_kernels = 2
+api.render_frame_device(batch, cam.view_projection(), cam.position, cfg, VD, ctx)
+print("kernel ms", api.frame_kernel_times(ctx))
+cap = 1 << 17
+out = np.zeros((cap, 14), dtype=np.uint64)
+n = C.c_int32()
+ctx.check(ctx.lib.vx_frame_trace(ctx.handle, out.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
+t = out[:n.value].astype(np.int64)
+tile, part, parts = t[:, 0], t[:, 1] & 0xffff, t[:, 1] >> 16
+t0, t1, sm, nsrc = t[:, 2], t[:, 3], t[:, 4], t[:, 5]
+base = t0.min()
+dur = (t1 - t0) / 1000.0
+print(f"items {n.value}  span {(t1.max() - base) / 1000.0:.1f} us  first start {(t0.min() - base) / 1000:.1f}  last start {(t0.max() - base) / 1000:.1f} us")
+print("item duration us: mean %.2f  median %.2f  p90 %.2f  max %.2f  sum %.0f" % (dur.mean(), np.median(dur), np.percentile(dur, 90), dur.max(), dur.sum()))
+for lo, hi in ((0, 0), (1, 8), (9, 64), (65, 255), (256, 100000)):
+    m = (nsrc >= lo) & (nsrc <= hi)
+    if m.any():
+        print(f"  n_src {lo:4d}..{hi:<6d}: {int(m.sum()):5d} items  mean {dur[m].mean():6.2f}  max {dur[m].max():6.2f} us")
+ph = t[:, 6:9] - t[:, 2:3]
+m = nsrc > 0
+print("phase ends after item start (us, items with work): keys %.2f  expansion %.2f  first task round %.2f  end %.2f" % tuple(
+    [float(np.mean(ph[m, k])) / 1000 for k in range(3)] + [float(dur[m].mean())]))
+cyc = t[:, 9:13].astype(np.float64)
+mm = m & (cyc[:, 3] > 0)
+print("thread-0 first task (cycles, mean over %d items): load %.0f  edges %.0f  span+jump %.0f  pixels %.0f  npix %.1f" % (
+    int(mm.sum()), cyc[mm, 0].mean(), cyc[mm, 1].mean(), cyc[mm, 2].mean(), cyc[mm, 3].mean(), t[mm, 13].mean()))
+order = np.argsort(-dur)[:12]
+for i in order:
+    print(f"  slow: item {i} tile ({tile[i] % ((W + 127) // 128)},{tile[i] // ((W + 127) // 128)}) part {part[i]}/{parts[i]} n_src {nsrc[i]} dur {dur[i]:.1f} us start {(t0[i] - base) / 1000:.1f} sm {sm[i]}")
+late = np.argsort(-t1)[:8]
+for i in late:
+    print(f"  late: item {i} tile ({tile[i] % ((W + 127) // 128)},{tile[i] // ((W + 127) // 128)}) part {part[i]}/{parts[i]} n_src {nsrc[i]} dur {dur[i]:.1f} us end {(t1[i] - base) / 1000:.1f}")
+so = np.zeros((148 * 12, 8), dtype=np.uint64)
+ns = C.c_int32()
+ctx.check(ctx.lib.vx_frame_setup_trace(ctx.handle, so.ctypes.data_as(C.c_void_p), so.shape[0], C.byref(ns)))
+so = so[:ns.value].astype(np.int64)
+so = so[so[:, 0] > 0]
+b0 = so[:, 0].min()
+rel = lambda c: (so[:, c] - b0) / 1000.0
+print(f"setup: {so.shape[0]} working CTAs, units/CTA max {so[:, 7].max()}; start mean {rel(0).mean():.1f} max {rel(0).max():.1f} | ranked mean {rel(1).mean():.1f} max {rel(1).max():.1f} | "
+      f"projected mean {rel(2).mean():.1f} max {rel(2).max():.1f} | binned mean {rel(3).mean():.1f} max {rel(3).max():.1f} | done mean {rel(4).mean():.1f} max {rel(4).max():.1f}")
+last = so[so[:, 5] > 0]
+if last.shape[0]:
+    print(f"setup plan: start {(last[0, 5] - b0) / 1000:.1f} end {(last[0, 6] - b0) / 1000:.1f} us;  raster first item starts {(base - b0) / 1000:.1f} us after the first setup CTA")
+st = api.frame_stats(ctx)
+print("survivors", st.n_survivors, "tris", st.n_triangles, "entries", st.n_bin_entries, "max_bin", st.reserved[0], "items", st.reserved[1])
+batch.release()
+ctx.close()
