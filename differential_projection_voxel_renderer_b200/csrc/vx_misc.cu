@@ -161,11 +161,21 @@ __global__ void selftest_division_kernel(unsigned long long seed, unsigned long 
             ua = (ua & 0xFFF80000u);
             ub = (ub & 0xFFF80000u);
         }
+        else if (mode == 3) { // texel division: denominators of the raster path, numerators down to zero / subnormals
+            ub = (ub & 0x807FFFFFu) | ((87u + (ub >> 23) % 103u) << 23);
+            ua = (ua & 0x807FFFFFu) | (((ua >> 23) % 190u) << 23);
+        }
         const float a = __uint_as_float(ua), b = __uint_as_float(ub);
         bool ok = true;
-        const float q = vx_div_fast(a, b, ok);
         const float ref = a / b;
         cnt++;
+        if (mode == 3) {
+            const float q = vx_div_texel(a, b, ok);
+            if (!ok) fb++;
+            else if ((vx_f2i(q * 8.0f) & 7) != (vx_f2i(ref * 8.0f) & 7)) bad++;
+            continue;
+        }
+        const float q = vx_div_fast(a, b, ok);
         if (!ok) fb++;
         else if (__float_as_uint(q) != __float_as_uint(ref) && !(q == 0.0f && ref == 0.0f)) bad++;
     }

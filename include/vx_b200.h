@@ -214,8 +214,9 @@ VX_API int vx_frame_kernel_times(VxContext *ctx, float ms_out[4]);
  * keys-ready ns, first-expansion ns, first-task-round ns, then for thread 0's first task the clock cycles spent on
  * record load, edge setup, span setup + jump, pixel walk, and its pixel count. */
 VX_API int vx_frame_trace(VxContext *ctx, uint64_t *out, int32_t cap_items, int32_t *n_items);
-/* Same for the setup kernel: 8 x u64 per CTA = start, ranked, projected, binned, done (ns), plan start, plan end (last
- * CTA only), units processed.  CTAs that had no unit stay all-zero. */
+/* Same for the setup kernel: 12 x u64 per CTA = start, ranked, projected, binned, done (ns), plan start, plan end (last
+ * CTA only), units processed, counted, ranges reserved, plan counters loaded, plan items written.  CTAs that had no
+ * unit stay all-zero. */
 VX_API int vx_frame_setup_trace(VxContext *ctx, uint64_t *out, int32_t cap_ctas, int32_t *n_ctas);
 /* Diagnostics: triangles binned per 128x8 tile in the last frame (row-major tile grid, ntx x nty). */
 VX_API int vx_frame_bin_counts(VxContext *ctx, uint32_t *counts_out, int32_t cap, int32_t *ntx, int32_t *nty);
@@ -250,7 +251,8 @@ VX_API int vx_project_mesh_vertices(VxContext *ctx, const VxMeshBatch *batch, in
 
 /* The raster kernels divide with an inlined, branch-free copy of nvcc's IEEE division fast path behind an explicit
  * exponent guard (vx_math.cuh: vx_div_fast).  This runs it against the `/` operator on n_pairs pseudo-random operand
- * pairs (mode 0: any bit patterns, 1: magnitudes of the raster path, 2: short mantissas) and returns
+ * pairs (mode 0: any bit patterns, 1: magnitudes of the raster path, 2: short mantissas; 3: the texel-lookup variant
+ * vx_div_texel, compared on the texel index) and returns
  * counters_out = {mismatches among guard-accepted pairs (must be 0), pairs sent to the fallback, pairs tested}. */
 VX_API int vx_selftest_division(VxContext *ctx, uint64_t seed, uint64_t n_pairs, int32_t mode, uint64_t counters_out[3]);
 

@@ -287,11 +287,11 @@ def test_hyper_pipeline_projection(ctx, ob):
 def test_branch_free_division_matches_ieee(ctx):
     """vx_div_fast (vx_math.cuh) must return the bits of the `/` operator for every operand pair its guard accepts."""
     import ctypes as C
-    for mode, n in ((0, 1 << 28), (1, 1 << 30), (2, 1 << 28)):
+    for mode, n in ((0, 1 << 28), (1, 1 << 30), (2, 1 << 28), (3, 1 << 30)):
         out = (C.c_uint64 * 3)()
         ctx.check(ctx.lib.vx_selftest_division(ctx.handle, 0x1234 + mode, n, mode, out))
         assert out[2] == n
         assert out[0] == 0, f"mode {mode}: {out[0]} mismatching quotients"
-        if mode == 1:
+        if mode in (1, 3):
             assert out[1] == 0, "the guard must accept the whole operating range of the raster path"
         print(f"mode {mode}: {out[2]} pairs, {out[1]} to the fallback, 0 mismatches")

@@ -55,7 +55,7 @@ for i in order:
 late = np.argsort(-t1)[:8]
 for i in late:
     print(f"  late: item {i} tile ({tile[i] % ((W + 127) // 128)},{tile[i] // ((W + 127) // 128)}) part {part[i]}/{parts[i]} n_src {nsrc[i]} dur {dur[i]:.1f} us end {(t1[i] - base) / 1000:.1f}")
-so = np.zeros((148 * 12, 8), dtype=np.uint64)
+so = np.zeros((148 * 12, 12), dtype=np.uint64)
 ns = C.c_int32()
 ctx.check(ctx.lib.vx_frame_setup_trace(ctx.handle, so.ctypes.data_as(C.c_void_p), so.shape[0], C.byref(ns)))
 so = so[:ns.value].astype(np.int64)
@@ -63,10 +63,10 @@ so = so[so[:, 0] > 0]
 b0 = so[:, 0].min()
 rel = lambda c: (so[:, c] - b0) / 1000.0
 print(f"setup: {so.shape[0]} working CTAs, units/CTA max {so[:, 7].max()}; start mean {rel(0).mean():.1f} max {rel(0).max():.1f} | ranked mean {rel(1).mean():.1f} max {rel(1).max():.1f} | "
-      f"projected mean {rel(2).mean():.1f} max {rel(2).max():.1f} | binned mean {rel(3).mean():.1f} max {rel(3).max():.1f} | done mean {rel(4).mean():.1f} max {rel(4).max():.1f}")
+      f"projected mean {rel(2).mean():.1f} max {rel(2).max():.1f} | counted mean {rel(8).mean():.1f} max {rel(8).max():.1f} | reserved mean {rel(9).mean():.1f} max {rel(9).max():.1f} | binned mean {rel(3).mean():.1f} max {rel(3).max():.1f} | done mean {rel(4).mean():.1f} max {rel(4).max():.1f}")
 last = so[so[:, 5] > 0]
 if last.shape[0]:
-    print(f"setup plan: start {(last[0, 5] - b0) / 1000:.1f} end {(last[0, 6] - b0) / 1000:.1f} us;  raster first item starts {(base - b0) / 1000:.1f} us after the first setup CTA")
+    print(f"setup plan: start {(last[0, 5] - b0) / 1000:.1f} loaded {(last[0, 10] - b0) / 1000:.1f} written {(last[0, 11] - b0) / 1000:.1f} end {(last[0, 6] - b0) / 1000:.1f} us;  raster first item starts {(base - b0) / 1000:.1f} us after the first setup CTA")
 st = api.frame_stats(ctx)
 print("survivors", st.n_survivors, "tris", st.n_triangles, "entries", st.n_bin_entries, "max_bin", st.reserved[0], "items", st.reserved[1])
 batch.release()
