@@ -71,6 +71,8 @@ PROTOTYPES = {
     "vx_device_synchronize": (C.c_int, [_P]),
     "vx_context_stream": (_P, [_P]),
     "vx_context_launch_count": (C.c_int64, [_P]),
+    "vx_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    "vx_host_free": (None, [_P, _P]),
     "vx_mesh_chunks": (C.c_int, [_P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
     "vx_mesh_chunks_device": (C.c_int, [_P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
     "vx_remesh_chunks_device": (C.c_int, [_P, _P, _P, _P, _P]),

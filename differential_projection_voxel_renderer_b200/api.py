@@ -40,6 +40,7 @@ class Context:
             raise VxError(rc, self.lib.vx_error_string(rc).decode())
         self.handle = h
         self.device = int(device)
+        self._host_allocs = []
 
     def check(self, rc: int):
         if rc != 0:
@@ -60,8 +61,22 @@ class Context:
     def set_atlas(self, atlas: VxAtlas):
         self.check(self.lib.vx_set_atlas(self.handle, C.byref(atlas)))
 
+    def host_array(self, shape, dtype) -> np.ndarray:
+        """Array in device-mapped page-locked host memory (vx_host_alloc): passed as color_out / depth_out of
+        render_frame it is written by the raster kernel directly.  Lives until the context is closed."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self.check(self.lib.vx_host_alloc(self.handle, n, C.byref(p)))
+        self._host_allocs.append(p)
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
     def close(self):
         if getattr(self, "handle", None):
+            for p in getattr(self, "_host_allocs", []):
+                self.lib.vx_host_free(self.handle, p)
+            self._host_allocs = []
             self.lib.vx_context_destroy(self.handle)
             self.handle = None
 
@@ -138,6 +153,7 @@ class MeshBatch:
         self.ctx = ctx
         self.handle = handle
         self._host = None
+        self._n_chunks = None
 
     def info(self) -> VxMeshBatchInfo:
         info = VxMeshBatchInfo()
@@ -342,8 +358,10 @@ class Rasterizer:
 
 
 def render_frame(batch: MeshBatch, view_proj, camera_position, cfg: VxFrameConfig, mesh_ids=None, view_distance: int = 0,
-                 color_out=None, depth_out=None, want_depth: bool = True, ctx: Optional[Context] = None):
-    """main.rs:379-608 (+ :283-297, :368-377).  Returns (color (rows,W) u32, depth (rows,W) f32 or None, survivors i32)."""
+                 color_out=None, depth_out=None, want_depth: bool = True, ctx: Optional[Context] = None, survivors_out=None):
+    """main.rs:379-608 (+ :283-297, :368-377).  Returns (color (rows,W) u32, depth (rows,W) f32 or None, survivors i32).
+    color_out / depth_out allocated with Context.host_array (device-mapped page-locked memory) are written by the
+    raster kernel in place; ordinary arrays are filled by a device-to-host copy."""
     ctx = ctx or batch.ctx
     vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
     cam = np.ascontiguousarray(camera_position, dtype=np.float32).reshape(3)
@@ -358,12 +376,14 @@ def render_frame(batch: MeshBatch, view_proj, camera_position, cfg: VxFrameConfi
         cap = max(1, n)
     else:
         n = -1
-        cap = max(1, batch.info().n_chunks)
-    surv = np.zeros(cap, dtype=np.int32)
+        if batch._n_chunks is None:
+            batch._n_chunks = int(batch.info().n_chunks)
+        cap = max(1, batch._n_chunks)
+    surv = survivors_out if survivors_out is not None else np.empty(cap, dtype=np.int32)
     ns = C.c_int32(0)
     ctx.check(ctx.lib.vx_render_frame(ctx.handle, batch.handle, _p(mesh_ids), n, _p(vp), _p(cam), int(view_distance), C.byref(cfg),
                                       _p(color_out), _p(depth_out), _p(surv), C.byref(ns)))
-    return color_out, depth_out, surv[:ns.value].copy()
+    return color_out, depth_out, (surv[:ns.value] if survivors_out is not None else surv[:ns.value].copy())
 
 
 def render_frame_device(batch: MeshBatch, view_proj, camera_position, cfg: VxFrameConfig, view_distance: int,

@@ -25,6 +25,7 @@
 #ifndef VX_B200_H
 #define VX_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -135,6 +136,13 @@ VX_API void *vx_context_stream(VxContext *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 VX_API int64_t vx_context_launch_count(const VxContext *ctx);
 
+/* Page-locked host memory mapped into the device address space (cudaHostAllocMapped | Portable).  Frame buffers
+ * allocated here (or with cudaHostAlloc / cudaHostRegister by the caller) are written directly by the raster kernel
+ * when passed to vx_render_frame: no staging copy, the PCIe writes overlap rasterization.  The Rust side backs
+ * `Framebuffer::color_buffer` / `depth_buffer` (framebuffer.rs:197-245) with it. */
+VX_API int vx_host_alloc(VxContext *ctx, size_t bytes, void **out);
+VX_API void vx_host_free(VxContext *ctx, void *p);
+
 /* ---- meshing ---------------------------------------------------------- */
 
 /* BinaryGreedyMesher::mesh_world (binary_greedy.rs:62-78) / mesh_chunk_in_world (:83) /
@@ -193,8 +201,9 @@ VX_API int vx_set_atlas(VxContext *ctx, const VxAtlas *atlas);
  *                 with n_meshes < 0 to run filter A on the device over the batch's own positions
  *                 (view_distance then required)
  *   color_out     rows x width u32 ARGB (may be NULL), depth_out rows x width f32 (may be NULL),
- *                 rows = stripe_rows or height
- *   survivors_out draw order (capacity n_meshes / n_chunks), may be NULL */
+ *                 rows = stripe_rows or height.  Device-mapped page-locked buffers (vx_host_alloc) are written in
+ *                 place by the kernel; other host memory is filled by a copy from the device framebuffer
+ *   survivors_out draw order (capacity n_meshes / n_chunks; entries past *n_survivors are undefined), may be NULL */
 VX_API int vx_render_frame(VxContext *ctx, const VxMeshBatch *batch, const int32_t *mesh_ids, int32_t n_meshes,
                     const float vp[16], const float cam_pos[3], int32_t view_distance, const VxFrameConfig *cfg,
                     uint32_t *color_out, float *depth_out, int32_t *survivors_out, int32_t *n_survivors);

@@ -295,3 +295,24 @@ def test_branch_free_division_matches_ieee(ctx):
         if mode in (1, 3):
             assert out[1] == 0, "the guard must accept the whole operating range of the raster path"
         print(f"mode {mode}: {out[2]} pairs, {out[1]} to the fallback, 0 mismatches")
+
+
+def test_mapped_host_framebuffer_is_written_in_place(ctx, ob, scene5):
+    """Device-mapped page-locked output buffers (vx_host_alloc) take the no-copy path: same frame, bit for bit."""
+    _, p, batch, ref = scene5
+    w, h = 640, 360
+    cam = vx_scenes.path_camera(1, w, h)
+    vp, ids, oc, od, osurv = oracle_frame(ob, ref, p, cam, w, h, 5)
+    cfg = api.default_frame_config(w, h)
+    color = ctx.host_array((h, w), np.uint32)
+    depth = ctx.host_array((h, w), np.float32)
+    color[...] = 0
+    depth[...] = 0
+    c, d, surv = api.render_frame(batch, vp, cam.position, cfg, mesh_ids=ids, color_out=color, depth_out=depth, ctx=ctx)
+    assert c is color and d is depth
+    assert np.array_equal(surv, osurv)
+    assert np.array_equal(color, oc) and np.array_equal(depth.view(np.uint32), od.view(np.uint32))
+    # colour in mapped memory, depth through the copy path
+    color[...] = 0
+    c, d, _ = api.render_frame(batch, vp, cam.position, cfg, mesh_ids=ids, color_out=color, ctx=ctx)
+    assert np.array_equal(color, oc) and np.array_equal(d.view(np.uint32), od.view(np.uint32))
