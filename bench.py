@@ -221,8 +221,8 @@ def run_cuda(args):
     cfg = api.default_frame_config(W, H)
     rows_per = (H + world_size - 1) // world_size
     if world_size > 1:
-        cfg.stripe_y0 = rank * rows_per
-        cfg.stripe_rows = max(0, min(rows_per, H - rank * rows_per))
+        from differential_projection_voxel_renderer_b200.sharding import stripe_of
+        cfg.stripe_y0, cfg.stripe_rows = stripe_of(H, rank, world_size)  # framebuffer.rs:403-427
     cfg_async = api.VxFrameConfig.from_buffer_copy(cfg)
     cfg_async.async_submit = 1
 
@@ -288,6 +288,75 @@ def run_cuda(args):
     fps = 1000.0 / ms_per_step
     api.frame_stats(ctx)  # surfaces an overflow of an async frame, if any
 
+    # ---- chunk-sharded remesh sweep (BASELINE cfg 4): rank r re-meshes the chunks k with k % N == r; the world's voxel
+    #      array is replicated, so halos need no exchange and there is no collective on the path (weak in the sense
+    #      that more GPUs are for more chunks; here the world is fixed, so the line is total chunks / max time)
+    from differential_projection_voxel_renderer_b200 import sharding
+    sub_ids = sharding.chunk_shard(n_chunks, rank, world_size)
+    d_sub = torch.from_numpy(sub_ids).to(dev)
+    sub_batch = api.BinaryGreedyMesher.mesh_batch_subset(d_vox.data_ptr(), d_pos.data_ptr(), d_nb.data_ptr(), 0, n_chunks,
+                                                         d_sub.data_ptr(), int(sub_ids.size), ctx)
+
+    def remesh_shard():
+        api.BinaryGreedyMesher.mesh_batch_subset(d_vox.data_ptr(), d_pos.data_ptr(), d_nb.data_ptr(), 0, n_chunks,
+                                                 d_sub.data_ptr(), int(sub_ids.size), ctx, batch=sub_batch)
+
+    for _ in range(3):
+        remesh_shard()
+    ctx.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sh_ms = []
+    for _ in range(20):
+        flush_l2()
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        remesh_shard()
+        b2.record(stream)
+        torch.cuda.synchronize()
+        sh_ms.append(a.elapsed_time(b2))
+    shard_ms = float(np.mean(sh_ms))
+    if dist is not None:
+        t = torch.tensor([shard_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        shard_ms = float(t.item())
+    sharded_chunks_per_s = n_chunks / (shard_ms * 1e-3)
+    sub_batch.release()
+
+    # ---- e2e at N > 1: every rank renders its stripe through the device API (VP + camera + config uploaded per call),
+    #      the stripes are gathered to GPU0 over NVLink and rank 0 reads the composed frame back into page-locked host
+    #      memory, every step; wall clock between barriers, max over ranks
+    e2e_multi = None
+    if world_size > 1:
+        frame_dev = torch.empty((world_size * rows_per, W), dtype=torch.int32, device=dev) if rank == 0 else None
+        host_frame = torch.empty((H, W), dtype=torch.int32).pin_memory() if rank == 0 else None
+        gath = [frame_dev[r * rows_per:(r + 1) * rows_per] for r in range(world_size)] if rank == 0 else None
+
+        def step_e2e():
+            api.render_frame_device(batch, vp, cam.position, cfg_async, VD, ctx)
+            dc, dd, rws, wdt = api.framebuffer_device(ctx)
+            with torch.cuda.stream(stream):
+                src = torch.as_tensor(_Cai(dc, (rws, wdt), "<i4"), device=dev)
+                my_stripe[:rws].copy_(src)
+                dist.gather(my_stripe, gath, dst=0)
+                if rank == 0:
+                    host_frame.copy_(frame_dev[:H], non_blocking=True)
+            ctx.synchronize()
+
+        for _ in range(3):
+            step_e2e()
+        ne2e = max(20, min(K, 200))
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(ne2e):
+            step_e2e()
+        dist.barrier()
+        torch.cuda.synchronize()
+        el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        e2e_multi = ne2e / float(el.item())
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -351,6 +420,8 @@ def run_cuda(args):
         wall = time.perf_counter() - t0
         e2e_ms = max(s0.elapsed_time(s1), wall * 1000.0) / ne2e
         e2e_val = 1000.0 / e2e_ms
+    else:
+        e2e_val = e2e_multi
 
     # ---- second BASELINE metric: chunks meshed / s (whole-world remesh sweep, inputs resident) -------------------
     def remesh():
@@ -414,7 +485,7 @@ def run_cuda(args):
         "clocks": clocks,
         "gpu_launches": int(l1 - l0),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "note": "api.render_frame -> vx_render_frame, one synchronous call per frame: VP + camera + config in; the ARGB frame lands in page-locked host memory (written over PCIe by the raster kernel itself, no staging copy) together with the draw order; the call returns after the stream has drained"},
+                "note": ("per step every rank renders its stripe (vx_render_frame_device), NCCL gather to GPU0, rank 0 copies the composed ARGB frame to page-locked host memory; wall clock between barriers, max over ranks" if world_size > 1 else "api.render_frame -> vx_render_frame, one synchronous call per frame: VP + camera + config in; the ARGB frame lands in page-locked host memory (written over PCIe by the raster kernel itself, no staging copy) together with the draw order; the call returns after the stream has drained")},
         "roofline": {"bound": "hbm", "kernel": knames[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(top_bytes), "kernel_ms": float(kms[top]),
@@ -428,6 +499,8 @@ def run_cuda(args):
             "launches_per_frame": int(launches_per_frame),
             "frame_algorithmic_bytes": int(b_frame), "frame_hbm_frac": (b_frame / (ms_per_step * 1e-3) / 1e9) / peak,
             "chunks_meshed_per_sec": chunks_per_s, "remesh_world_ms": mesh_ms, "remesh_world_chunks": n_chunks,
+            "chunks_meshed_per_sec_sharded": sharded_chunks_per_s, "remesh_sharded_ms_max_over_ranks": shard_ms,
+            "remesh_sharding": f"chunk id modulo {world_size} GPUs, voxels replicated, no collective",
             "remesh_algorithmic_GBps": mesh_gbs, "remesh_hbm_frac": mesh_gbs / peak,
             "chunks_meshed_per_sec_large_batch": big_cps, "large_batch": f"{rep} copies of one terrain chunk, no neighbours (BASELINE configs[0] replicated, 512 MiB of voxels)",
             "large_batch_algorithmic_GBps": big_gbs, "large_batch_hbm_frac": big_gbs / peak,

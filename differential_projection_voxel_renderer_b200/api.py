@@ -237,6 +237,20 @@ class BinaryGreedyMesher:
         return MeshBatch(ctx, h)
 
     @staticmethod
+    def mesh_batch_subset(d_voxels: int, d_positions: int, d_neighbors: int, d_uniform_flags: int, n_chunks: int,
+                          d_subset: int, n_subset: int, ctx: Context, batch: Optional[MeshBatch] = None) -> MeshBatch:
+        """One rank's share of a chunk-sharded remesh (vx_mesh_chunk_subset_device): device pointers of the replicated
+        world arrays + the chunk ids to mesh.  Pass the returned batch back in to re-mesh without allocating."""
+        h = batch.handle if batch is not None else C.c_void_p()
+        ctx.check(ctx.lib.vx_mesh_chunk_subset_device(ctx.handle, C.c_void_p(d_voxels), C.c_void_p(d_positions or None),
+                                                      C.c_void_p(d_neighbors or None), C.c_void_p(d_uniform_flags or None),
+                                                      int(n_chunks), C.c_void_p(d_subset), int(n_subset), C.byref(h)))
+        if batch is not None:
+            batch._host = None
+            return batch
+        return MeshBatch(ctx, h)
+
+    @staticmethod
     def mesh_chunk(voxels, position=(0, 0, 0), ctx: Optional[Context] = None) -> Optional[ChunkMesh]:
         """binary_greedy.rs:55: no neighbour information, borders are air."""
         b = BinaryGreedyMesher.mesh_batch(np.asarray(voxels).reshape(1, CHUNK_VOLUME), [position], None, None, ctx)

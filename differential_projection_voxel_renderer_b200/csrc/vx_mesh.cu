@@ -21,6 +21,8 @@
 //            and writes the 3-byte TinyQuads at their final position.
 #include "vx_common.cuh"
 
+#include <vector>
+
 namespace {
 
 constexpr int MESH_THREADS = 256;
@@ -122,7 +124,9 @@ struct ChunkArgs {
     const uint8_t *voxels;
     const int32_t *neighbors;
     const uint8_t *uniform_flags;
-    int32_t n_chunks;
+    int32_t n_chunks;       // chunks in the voxel / neighbour arrays (what neighbour indices refer to)
+    const int32_t *subset;  // chunk ids to mesh (a shard of the world), or null = all n_chunks
+    int32_t n_out;          // chunks meshed = entries of the output arrays
     uint8_t *quads;
     unsigned long long cap_quads;
     uint32_t *quad_base, *quad_count, *slice_offsets;
@@ -256,16 +260,17 @@ __global__ void __launch_bounds__(MESH_THREADS) mesh_chunks_kernel(ChunkArgs a) 
     __shared__ MeshSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int chunk = blockIdx.x; chunk < a.n_chunks; chunk += gridDim.x) {
-        uint32_t *so = a.slice_offsets + (size_t)chunk * 198;
-        int32_t *ab = a.face_aabb + (size_t)chunk * 36;
+    for (int oi = blockIdx.x; oi < a.n_out; oi += gridDim.x) {
+        const int chunk = a.subset ? a.subset[oi] : oi; // input chunk; outputs are indexed by oi
+        uint32_t *so = a.slice_offsets + (size_t)oi * 198;
+        int32_t *ab = a.face_aabb + (size_t)oi * 36;
         if (a.uniform_flags && a.uniform_flags[chunk]) { // Uniform chunk -> None (binary_greedy.rs:87)
             for (int i = tid; i < 198; i += MESH_THREADS) so[i] = 0;
             if (tid < 36) ab[tid] = (tid % 6) < 3 ? 32 : 0;
             if (tid == 0) {
-                a.quad_base[chunk] = 0;
-                a.quad_count[chunk] = 0;
-                a.has_mesh[chunk] = 0;
+                a.quad_base[oi] = 0;
+                a.quad_count[oi] = 0;
+                a.has_mesh[oi] = 0;
             }
             continue;
         }
@@ -335,9 +340,9 @@ __global__ void __launch_bounds__(MESH_THREADS) mesh_chunks_kernel(ChunkArgs a) 
             sm.overflow = (base + run > a.cap_quads) ? 1u : 0u;
             if (sm.overflow) atomicExch(a.cursor + 2, 1ull);
             sm.base = (uint32_t)base;
-            a.quad_base[chunk] = (uint32_t)base;
-            a.quad_count[chunk] = run;
-            a.has_mesh[chunk] = run ? 1 : 0; // mesh.is_empty() -> None (binary_greedy.rs:116-120)
+            a.quad_base[oi] = (uint32_t)base;
+            a.quad_count[oi] = run;
+            a.has_mesh[oi] = run ? 1 : 0; // mesh.is_empty() -> None (binary_greedy.rs:116-120)
         }
         __syncthreads();
         if (tid < 192) {
@@ -396,14 +401,16 @@ int batch_alloc(VxContext *ctx, VxMeshBatch *b, int32_t n, int64_t cap_quads) {
 }
 
 int run_mesher(VxContext *ctx, const uint8_t *d_vox, const int32_t *d_nb, const uint8_t *d_uf, VxMeshBatch *b,
-               bool allow_regrow) {
+               bool allow_regrow, const int32_t *d_subset = nullptr, int32_t n_total = -1) {
     for (int attempt = 0; attempt < 2; ++attempt) {
         VX_CUDA(ctx, cudaMemsetAsync(b->cursor.ptr, 0, sizeof(unsigned long long) * 4, ctx->stream));
         ChunkArgs a;
         a.voxels = d_vox;
         a.neighbors = d_nb;
         a.uniform_flags = d_uf;
-        a.n_chunks = b->n_chunks;
+        a.n_chunks = n_total >= 0 ? n_total : b->n_chunks;
+        a.subset = d_subset;
+        a.n_out = b->n_chunks;
         a.quads = b->quads.as<uint8_t>();
         a.cap_quads = (unsigned long long)b->cap_quads;
         a.quad_base = b->quad_base.as<uint32_t>();
@@ -467,6 +474,50 @@ int vx_mesh_chunks_device(VxContext *ctx, const uint8_t *d_voxels, const int32_t
         return rc;
     }
     *out = b;
+    return VX_OK;
+}
+
+int vx_mesh_chunk_subset_device(VxContext *ctx, const uint8_t *d_voxels, const int32_t *d_positions,
+                                const int32_t *d_neighbors, const uint8_t *d_uniform_flags, int32_t n_chunks,
+                                const int32_t *d_subset, int32_t n_subset, VxMeshBatch **batch_inout) {
+    if (!ctx || !batch_inout || n_chunks < 0 || n_subset < 0 || (n_subset > 0 && (!d_voxels || !d_subset)))
+        return vx_fail(ctx, VX_ERR_INVALID, "vx_mesh_chunk_subset_device: bad argument");
+    if ((reinterpret_cast<uintptr_t>(d_voxels) & 15) != 0) return vx_fail(ctx, VX_ERR_INVALID, "voxels must be 16-byte aligned");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (*batch_inout) { // steady state: re-mesh the same shard into the existing batch, no allocation
+        if ((*batch_inout)->n_chunks != n_subset) return vx_fail(ctx, VX_ERR_INVALID, "batch was created for another subset size");
+        if (n_subset == 0) return VX_OK;
+        return run_mesher(ctx, d_voxels, d_neighbors, d_uniform_flags, *batch_inout, false, d_subset, n_chunks);
+    }
+    VxMeshBatch *b = new VxMeshBatch();
+    int rc = batch_alloc(ctx, b, n_subset, (int64_t)(n_subset > 0 ? n_subset : 1) * 512);
+    if (rc == VX_OK && n_subset > 0) {
+        // positions of the subset, gathered on the host side of the stream (small)
+        if (d_positions) {
+            std::vector<int32_t> ids((size_t)n_subset), pos((size_t)n_chunks * 3), sub((size_t)n_subset * 3);
+            cudaError_t e = cudaMemcpyAsync(ids.data(), d_subset, sizeof(int32_t) * (size_t)n_subset, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(pos.data(), d_positions, sizeof(int32_t) * 3 * (size_t)n_chunks, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e == cudaSuccess) {
+                for (int32_t i = 0; i < n_subset; ++i) {
+                    if (ids[i] < 0 || ids[i] >= n_chunks) { rc = vx_fail(ctx, VX_ERR_INVALID, "subset id out of range"); break; }
+                    for (int k = 0; k < 3; ++k) sub[(size_t)i * 3 + k] = pos[(size_t)ids[i] * 3 + k];
+                }
+                if (rc == VX_OK) e = cudaMemcpyAsync(b->positions.ptr, sub.data(), sizeof(int32_t) * 3 * (size_t)n_subset, cudaMemcpyHostToDevice, ctx->stream);
+                if (rc == VX_OK && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            }
+            if (rc == VX_OK && e != cudaSuccess) rc = vx_cuda_fail(ctx, e, "subset positions", __FILE__, __LINE__);
+        } else {
+            cudaMemsetAsync(b->positions.ptr, 0, sizeof(int32_t) * 3 * (size_t)n_subset, ctx->stream);
+        }
+    }
+    if (rc == VX_OK && n_subset > 0) rc = run_mesher(ctx, d_voxels, d_neighbors, d_uniform_flags, b, true, d_subset, n_chunks);
+    if (rc == VX_OK && n_subset == 0) { b->total_quads = 0; b->n_meshes = 0; }
+    if (rc != VX_OK) {
+        vx_mesh_batch_release(ctx, b);
+        return rc;
+    }
+    *batch_inout = b;
     return VX_OK;
 }
 

@@ -160,6 +160,13 @@ VX_API int vx_mesh_chunks(VxContext *ctx, const uint8_t *voxels, const int32_t *
 VX_API int vx_mesh_chunks_device(VxContext *ctx, const uint8_t *d_voxels, const int32_t *d_positions,
                           const int32_t *d_neighbors, const uint8_t *d_uniform_flags, int32_t n_chunks,
                           VxMeshBatch **out);
+/* Chunk-sharded meshing (one rank of a multi-GPU remesh sweep): mesh only the chunks listed in
+ * d_subset (ids into the n_chunks-sized arrays, e.g. every world_size-th sorted chunk id).  The voxel / neighbour
+ * arrays are the whole world (replicated), so neighbour halos need no exchange; the batch has n_subset chunks in
+ * subset order.  *batch_inout == NULL: create it; else re-mesh into it (steady state, no allocation, no sync). */
+VX_API int vx_mesh_chunk_subset_device(VxContext *ctx, const uint8_t *d_voxels, const int32_t *d_positions,
+                                const int32_t *d_neighbors, const uint8_t *d_uniform_flags, int32_t n_chunks,
+                                const int32_t *d_subset, int32_t n_subset, VxMeshBatch **batch_inout);
 /* Re-mesh into an existing batch of the same n_chunks (steady-state remesh sweep: no allocation). */
 VX_API int vx_remesh_chunks_device(VxContext *ctx, const uint8_t *d_voxels, const int32_t *d_neighbors,
                             const uint8_t *d_uniform_flags, VxMeshBatch *batch);

@@ -182,3 +182,38 @@ def test_invalid_arguments_fail_loudly(ctx):
     import ctypes as C
     h = C.c_void_p()
     assert ctx.lib.vx_mesh_chunks(ctx.handle, None, None, None, None, 3, C.byref(h)) == -1
+
+
+def test_chunk_subset_meshing_matches_the_full_batch(ctx, ob):
+    """vx_mesh_chunk_subset_device (one rank of a chunk-sharded remesh): the shard's meshes equal the same chunks of
+    the full batch, with neighbour halos taken from chunks that are NOT in the shard."""
+    import torch
+    import vx_scenes
+    from differential_projection_voxel_renderer_b200 import sharding
+    pos, world, p, v, nb = vx_scenes.terrain_scene(4)
+    n = p.shape[0]
+    ref = ob.mesh_chunks(v, nb, None, p)
+    dev = torch.device("cuda", 0)
+    dv, dn, dp = torch.from_numpy(v).to(dev), torch.from_numpy(nb).to(dev), torch.from_numpy(p).to(dev)
+    shards = []
+    for world_size in (3,):
+        for r in range(world_size):
+            ids = sharding.chunk_shard(n, r, world_size)
+            dids = torch.from_numpy(ids).to(dev)
+            b = api.BinaryGreedyMesher.mesh_batch_subset(dv.data_ptr(), dp.data_ptr(), dn.data_ptr(), 0, n, dids.data_ptr(), ids.size, ctx)
+            got = b.download()
+            for j, cid in enumerate(ids.tolist()):
+                assert np.array_equal(b.chunk_quads(j).reshape(-1), ref.chunk_quads(cid).reshape(-1)), (r, cid)
+            assert np.array_equal(got["slice_offsets"], ref.slice_offsets[ids])
+            assert np.array_equal(got["face_aabb"], ref.face_aabb[ids])
+            # steady-state re-mesh into the same batch gives the same result
+            api.BinaryGreedyMesher.mesh_batch_subset(dv.data_ptr(), dp.data_ptr(), dn.data_ptr(), 0, n, dids.data_ptr(), ids.size, ctx, batch=b)
+            again = b.download()
+            assert np.array_equal(again["quad_count"], got["quad_count"])
+            for j, cid in enumerate(ids.tolist()):
+                assert np.array_equal(b.chunk_quads(j).reshape(-1), ref.chunk_quads(cid).reshape(-1)), ("remesh", r, cid)
+            shards.append(got)
+            b.release()
+        merged = sharding.merge_mesh_shards(shards, n, world_size)
+        assert np.array_equal(merged["quads"].reshape(-1), ref.quads.reshape(-1)[:merged["quads"].size])
+        assert np.array_equal(merged["quad_base"], ref.quad_base) and np.array_equal(merged["has_mesh"], ref.has_mesh)

@@ -1,0 +1,112 @@
+"""World-size-2 tests (gloo, CPU) of the multi-GPU host logic in sharding.py: chunk-sharded meshing results are
+all-gathered back into batch order, and stripe-sharded frames are gathered to rank 0.  The compute on
+each rank is done by the CPU oracle here (the GPU path does the same with CUDA kernels: tests/test_multi_gpu.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import vx_scenes
+from differential_projection_voxel_renderer_b200 import sharding
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _shard_of(full, ids):
+    """What a rank's mesher returns for its chunk subset: compact arrays in subset order."""
+    quads, base, cnt = [], [], []
+    run = 0
+    for cid in ids.tolist():
+        c = int(full.quad_count[cid])
+        base.append(run)
+        cnt.append(c)
+        quads.append(full.chunk_quads(cid).reshape(-1, 3))
+        run += c
+    return {"quads": np.concatenate(quads) if quads else np.zeros((0, 3), np.uint8),
+            "quad_base": np.asarray(base, np.uint32), "quad_count": np.asarray(cnt, np.uint32),
+            "slice_offsets": full.slice_offsets[ids], "face_aabb": full.face_aabb[ids], "has_mesh": full.has_mesh[ids]}
+
+
+def _worker(rank, world, port, w, h, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import binding as ob
+        pos, world_obj, p, v, nb = vx_scenes.terrain_scene(3)
+        n = p.shape[0]
+        full = ob.mesh_chunks(v, nb, None, p)  # every rank could mesh everything; it only keeps its shard
+        ids = sharding.chunk_shard(n, rank, world)
+        merged = sharding.all_gather_mesh_shards(_shard_of(full, ids), n)
+        assert np.array_equal(merged["quad_count"], full.quad_count)
+        assert np.array_equal(merged["quad_base"], full.quad_base)
+        assert np.array_equal(merged["quads"].reshape(-1), full.quads.reshape(-1)[:merged["quads"].size])
+        assert np.array_equal(merged["slice_offsets"], full.slice_offsets)
+        assert np.array_equal(merged["face_aabb"], full.face_aabb)
+        assert np.array_equal(merged["has_mesh"], full.has_mesh)
+
+        # stripe-sharded frame: each rank draws the sorted meshes into its rows only, rank 0 gets the gathered frame
+        cam = vx_scenes.path_camera(1, w, h)
+        vp = cam.view_projection()
+        vis = ob.cull_chunks(p, vp, cam.position, 3)
+        mesh_ids = np.flatnonzero((vis != 0) & (full.has_mesh != 0)).astype(np.int32)
+        cfg, atlas = ob.default_frame_config(w, h, n_threads=2), ob.default_atlas()
+        fc, fd, order = ob.render_frame(full, mesh_ids, vp, cam.position, cfg, atlas)
+        y0, rows = sharding.stripe_of(h, rank, world)
+        color = np.full((h, w), cfg.clear_color, dtype=np.uint32)
+        depth = np.full((h, w), np.inf, dtype=np.float32)
+        for m in order.tolist():
+            ob.render_mesh(full, int(m), vp, cfg, atlas, (0, y0, w, rows), color, depth)
+        frame = sharding.gather_stripes(torch.from_numpy(color[y0:y0 + rows].view(np.int32).copy()), h, w, dst=0)
+        dframe = sharding.gather_stripes(torch.from_numpy(depth[y0:y0 + rows].copy()), h, w, dst=0)
+        if rank == 0:
+            assert np.array_equal(frame.numpy().view(np.uint32), fc)
+            assert np.array_equal(dframe.numpy().view(np.uint32), fd.view(np.uint32))
+            assert int((fc != cfg.clear_color).sum()) > 500
+        else:
+            assert frame is None
+        dist.barrier()
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("hw", [(96, 160), (90, 161)])  # even split, and ragged rows / odd width
+def test_shards_and_stripes_world_size_2(tmp_path, hw):
+    h, w = hw
+    mp.spawn(_worker, args=(2, _free_port(), w, h, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_stripe_partition_matches_split_into_stripes():
+    """framebuffer.rs:403-427: ceil(H / n) rows per stripe, trailing stripes shorter or absent."""
+    for h in (1, 7, 90, 720, 2160):
+        for n in (1, 2, 3, 4, 8, 16):
+            per = (h + n - 1) // n
+            y, covered = 0, 0
+            for r in range(n):
+                y0, rows = sharding.stripe_of(h, r, n)
+                if y >= h:
+                    assert rows == 0
+                    continue
+                assert y0 == y and rows == min(per, h - y)
+                y += rows
+                covered += rows
+            assert covered == h
+
+
+def test_chunk_shards_partition_the_batch():
+    for n in (0, 1, 5, 818):
+        for world in (1, 2, 4, 8):
+            ids = np.concatenate([sharding.chunk_shard(n, r, world) for r in range(world)])
+            assert np.array_equal(np.sort(ids), np.arange(n))
