@@ -28,18 +28,26 @@ namespace {
 constexpr int MESH_THREADS = 256;
 constexpr int MESH_WARPS = MESH_THREADS / 32;
 constexpr int PS = 33; // padded row stride of the 32x32 word planes (bank-conflict free both ways)
+constexpr int STAGE_CAP = 128;          // quads one (face, slice) unit may stage per warp on the fast path
+constexpr int POOL_CAP = 2 * 32 * PS;   // quads of a chunk kept in shared memory on the fast path (aliases P0/P1)
 constexpr unsigned FULL = 0xffffffffu;
 
 struct MeshSmem {
-    uint32_t P0[32 * PS];        // [y*PS + z], bit x = block_type bit 0
-    uint32_t P1[32 * PS];        // [y*PS + z], bit x = block_type bit 1
-    uint32_t MX[2][3][32 * PS];  // [sign][type-1][x*PS + y], bit z : +-X exposure in greedy orientation
-    uint32_t halo[6][32];        // neighbour solid planes, see load_halos()
-    uint32_t cnt[192];           // quads per (face, slice)
-    uint32_t offs[192];          // exclusive offsets inside the chunk
+    // stage 1: [y*PS + z], bit x = block-type bit 0 / 1.  After stage 2 the space is the chunk's quad pool.
+    union {
+        struct { uint32_t P0[32 * PS], P1[32 * PS]; } p;
+        uint32_t pool[POOL_CAP];
+    } u;
+    uint32_t T0[32 * PS], T1[32 * PS]; // [x*PS + y], bits z: rows of the +-X units (lane = y) and +-Y units (lane = x)
+    uint32_t R0[32 * PS], R1[32 * PS]; // [z*PS + x], bits y: rows of the +-Z units (lane = x)
+    uint32_t halo[6][32];              // neighbour solid planes in unit orientation, see load_halos()
+    uint32_t stage[MESH_WARPS][STAGE_CAP];
+    uint32_t cnt[192];                 // quads per (face, slice)
+    uint32_t offs[192];                // exclusive offsets inside the chunk
+    uint32_t pstart[192];              // start of the unit's quads in the pool (fast path)
     uint32_t faceTot[6], faceBase[6];
     uint32_t faceRows[6], faceCols[6], faceSlices[6];
-    uint32_t base, total, overflow;
+    uint32_t base, total, overflow, pool_used, slow;
 };
 
 // 4 voxels (one per byte, values 0..3) -> 4 bits, voxel k -> bit k.  bit = 0 or 1 selects the type bit.
@@ -78,12 +86,22 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
     return x;
 }
 
-// Greedy merge of one 32x32 mask (binary_greedy.rs:683-807).  Lane = row, d = that row's bits.
-// EMIT=false: returns the quad count.  EMIT=true: writes TinyQuads (mesh.rs:283-307) of block type
-// `type` to out[3*(pos + k)]; if out4 != nullptr writes VxQuad {row, col, width, height} instead.
-template <bool EMIT>
+// TinyQuad::new (mesh.rs:283-307) as the three bytes b0 | b1 << 8 | b2 << 16
+__device__ __forceinline__ uint32_t pack_tinyquad(uint32_t u, uint32_t v, uint32_t w, uint32_t h, uint32_t type) {
+    const uint32_t b0 = u | ((v & 7u) << 5);
+    const uint32_t b1 = (v >> 3) | ((w - 1u) << 2);
+    const uint32_t b2 = (h - 1u) | (type << 6);
+    return b0 | (b1 << 8) | (b2 << 16);
+}
+
+// Greedy merge of one 32x32 mask (binary_greedy.rs:683-807).  Lane = row, d = that row's bits.  Returns the quad count.
+//   MODE 0: count only.
+//   MODE 1: write TinyQuads (mesh.rs:283-307) of block type `type` to out[3*(pos + k)]; if out4 != nullptr write
+//           VxQuad {row, col, width, height} instead.
+//   MODE 2: write packed TinyQuads (u32) to stage[pos + k] while pos + k < STAGE_CAP (keeps counting beyond).
+template <int MODE>
 __device__ __forceinline__ uint32_t greedy_warp(uint32_t d, int lane, uint32_t type, uint8_t *out, uint32_t pos,
-                                                VxQuad *out4) {
+                                                VxQuad *out4, uint32_t *stage) {
     uint32_t n = 0;
     uint32_t rows = __ballot_sync(FULL, d != 0);
     while (rows) {
@@ -101,17 +119,16 @@ __device__ __forceinline__ uint32_t greedy_warp(uint32_t d, int lane, uint32_t t
             const uint32_t below = r == 31 ? 0u : (ok >> (r + 1));
             const int ext = __ffs(~below) - 1; // consecutive rows r+1.. (bits >= 31-r are 0 -> terminates)
             if (lane > r && lane <= r + ext) d &= ~m;
-            if (EMIT) {
-                const uint32_t w = 1u + (uint32_t)ext;
+            const uint32_t w = 1u + (uint32_t)ext;
+            if (MODE == 1) {
                 if (out4) {
                     if (lane == 0) out4[pos + n] = VxQuad{(uint8_t)r, (uint8_t)col, (uint8_t)w, (uint8_t)h};
                 } else {
-                    const uint32_t b0 = (uint32_t)r | (((uint32_t)col & 7u) << 5);
-                    const uint32_t b1 = ((uint32_t)col >> 3) | ((w - 1u) << 2);
-                    const uint32_t b2 = ((uint32_t)h - 1u) | (type << 6);
-                    const uint32_t packed = b0 | (b1 << 8) | (b2 << 16);
+                    const uint32_t packed = pack_tinyquad((uint32_t)r, (uint32_t)col, w, (uint32_t)h, type);
                     if (lane < 3) out[3 * (size_t)(pos + n) + lane] = (uint8_t)(packed >> (8 * lane));
                 }
+            } else if (MODE == 2) {
+                if (lane == 0 && pos + n < (uint32_t)STAGE_CAP) stage[pos + n] = pack_tinyquad((uint32_t)r, (uint32_t)col, w, (uint32_t)h, type);
             }
             n++;
             cur &= ~m;
@@ -135,7 +152,9 @@ struct ChunkArgs {
     unsigned long long *cursor; // [0] quad cursor, [1] mesh counter, [2] overflow flag
 };
 
-// halo[f][i]: f=0/1 (+X/-X): i = y, bit z;  f=2/3 (+Y/-Y): i = z, bit x;  f=4/5 (+Z/-Z): i = y, bit x.
+// Neighbour solid planes.  First in load order: f=0/1 (+X/-X): i = y, bit z;  f=2/3 (+Y/-Y): i = z, bit x;
+// f=4/5 (+Z/-Z): i = y, bit x.  transpose_halos() then brings f = 2..5 into unit orientation:
+// f=2/3: i = x, bit z;  f=4/5: i = x, bit y  (f = 0/1 already are: i = y, bit z).
 __device__ void load_halos(MeshSmem &sm, const ChunkArgs &a, int chunk, int tid) {
     const int lane = tid & 31, warp = tid >> 5;
     // resolve the six neighbours (warp-uniform values, computed redundantly)
@@ -177,11 +196,12 @@ __device__ void load_halos(MeshSmem &sm, const ChunkArgs &a, int chunk, int tid)
             pack_row(__ldg(p), __ldg(p + 1), p0, p1);
             word = p0 | p1;
         }
-        sm.halo[f][i] = word;
+        // (i, bit x) -> (x, bit i): warps 0..3 hold exactly the four planes f = 2..5
+        sm.halo[f][lane] = transpose32(word, lane);
     }
 }
 
-// exposure words (bits x) of the three block types for voxel row (y,z) against neighbour solid word nbS
+// exposure words of the three block types of a row against the neighbour row's solid word
 __device__ __forceinline__ void exposure(uint32_t a0, uint32_t a1, uint32_t nbS, uint32_t e[3]) {
     const uint32_t open = ~nbS;
     e[0] = a0 & ~a1 & open; // Grass = 1
@@ -189,44 +209,41 @@ __device__ __forceinline__ void exposure(uint32_t a0, uint32_t a1, uint32_t nbS,
     e[2] = a0 & a1 & open;  // Stone = 3
 }
 
-// Row words (lane = row, bits = column) of unit (face, slice) for the three block types.
-// axis 1 (Y): rows x, cols z   axis 2 (Z): rows x, cols y   (binary_greedy.rs:446-458); axis 0 comes from MX.
-__device__ __forceinline__ void unit_rows_yz(const MeshSmem &sm, int face, int slice, int lane, uint32_t d[3]) {
+// Row words (lane = row, bits = column) of unit (face, slice) for the three block types, straight from the
+// pre-transposed planes: axis 0 (X): rows y, cols z;  axis 1 (Y): rows x, cols z;  axis 2 (Z): rows x, cols y
+// (binary_greedy.rs:446-458).
+__device__ __forceinline__ void unit_rows(const MeshSmem &sm, int face, int slice, int lane, uint32_t d[3]) {
     const int axis = face >> 1;
-    const bool positive = (face & 1) == 0;
+    const int ns = (face & 1) == 0 ? slice + 1 : slice - 1; // the neighbour slice along the face normal
+    const bool inside = ns >= 0 && ns < 32;
     uint32_t a0, a1, nbS;
-    if (axis == 1) { // lane = z
-        a0 = sm.P0[slice * PS + lane];
-        a1 = sm.P1[slice * PS + lane];
-        const int ny = positive ? slice + 1 : slice - 1;
-        if (ny >= 0 && ny < 32) nbS = sm.P0[ny * PS + lane] | sm.P1[ny * PS + lane];
-        else nbS = sm.halo[face][lane];
-    } else { // axis 2, lane = y
-        a0 = sm.P0[lane * PS + slice];
-        a1 = sm.P1[lane * PS + slice];
-        const int nz = positive ? slice + 1 : slice - 1;
-        if (nz >= 0 && nz < 32) nbS = sm.P0[lane * PS + nz] | sm.P1[lane * PS + nz];
-        else nbS = sm.halo[face][lane];
+    if (axis == 0) { // T[x][y], lane = y
+        a0 = sm.T0[slice * PS + lane];
+        a1 = sm.T1[slice * PS + lane];
+        nbS = inside ? (sm.T0[ns * PS + lane] | sm.T1[ns * PS + lane]) : sm.halo[face][lane];
+    } else if (axis == 1) { // T[x][y], lane = x
+        a0 = sm.T0[lane * PS + slice];
+        a1 = sm.T1[lane * PS + slice];
+        nbS = inside ? (sm.T0[lane * PS + ns] | sm.T1[lane * PS + ns]) : sm.halo[face][lane];
+    } else { // R[z][x], lane = x
+        a0 = sm.R0[slice * PS + lane];
+        a1 = sm.R1[slice * PS + lane];
+        nbS = inside ? (sm.R0[ns * PS + lane] | sm.R1[ns * PS + lane]) : sm.halo[face][lane];
     }
-    uint32_t e[3];
-    exposure(a0, a1, nbS, e);
-#pragma unroll
-    for (int t = 0; t < 3; ++t) d[t] = __any_sync(FULL, e[t] != 0) ? transpose32(e[t], lane) : 0u;
+    exposure(a0, a1, nbS, d);
 }
 
-template <bool EMIT>
+// Pass over the 192 (face, slice) units of the chunk, one warp per unit.
+//   MODE 2 (fast path): count, and stage / pool the quads in shared memory;  MODE 1 (slow path): re-run the merge and
+//   write the quads to their final place (only for chunks whose quads did not fit the pool).
+template <int MODE>
 __device__ __forceinline__ void process_units(MeshSmem &sm, const ChunkArgs &a, int tid) {
     const int lane = tid & 31, warp = tid >> 5;
     for (int unit = warp; unit < 192; unit += MESH_WARPS) {
         const int face = unit >> 5, slice = unit & 31;
         uint32_t d[3];
-        if (face < 2) {
-#pragma unroll
-            for (int t = 0; t < 3; ++t) d[t] = sm.MX[face][t][slice * PS + lane];
-        } else {
-            unit_rows_yz(sm, face, slice, lane, d);
-        }
-        if (!EMIT) {
+        unit_rows(sm, face, slice, lane, d);
+        if (MODE == 2) {
             uint32_t n = 0, rowsAny = 0, colsAny = 0;
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
@@ -234,29 +251,40 @@ __device__ __forceinline__ void process_units(MeshSmem &sm, const ChunkArgs &a, 
                 if (any) {
                     rowsAny |= any;
                     colsAny |= __reduce_or_sync(FULL, d[t]);
-                    n += greedy_warp<false>(d[t], lane, 0, nullptr, 0, nullptr);
+                    n += greedy_warp<2>(d[t], lane, (uint32_t)(t + 1), nullptr, n, nullptr, sm.stage[warp]);
                 }
             }
+            uint32_t start = 0;
             if (lane == 0) {
                 sm.cnt[unit] = n;
                 if (n) {
                     atomicOr(&sm.faceRows[face], rowsAny);
                     atomicOr(&sm.faceCols[face], colsAny);
                     atomicOr(&sm.faceSlices[face], 1u << slice);
+                    start = atomicAdd(&sm.pool_used, n);
+                    sm.pstart[unit] = start;
+                    if (n > (uint32_t)STAGE_CAP || start + n > (uint32_t)POOL_CAP) sm.slow = 1u;
                 }
+            }
+            if (n) {
+                start = __shfl_sync(FULL, start, 0);
+                __syncwarp();
+                if (n <= (uint32_t)STAGE_CAP && start + n <= (uint32_t)POOL_CAP)
+                    for (uint32_t i = lane; i < n; i += 32) sm.u.pool[start + i] = sm.stage[warp][i];
+                __syncwarp();
             }
         } else {
             if (sm.cnt[unit] == 0) continue;
             uint32_t pos = sm.base + sm.offs[unit];
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
-                if (__any_sync(FULL, d[t] != 0)) pos += greedy_warp<true>(d[t], lane, (uint32_t)(t + 1), a.quads, pos, nullptr);
+                if (__any_sync(FULL, d[t] != 0)) pos += greedy_warp<1>(d[t], lane, (uint32_t)(t + 1), a.quads, pos, nullptr, nullptr);
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(MESH_THREADS) mesh_chunks_kernel(ChunkArgs a) {
+__global__ void __launch_bounds__(MESH_THREADS, 5) mesh_chunks_kernel(ChunkArgs a) {
     __shared__ MeshSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -274,7 +302,7 @@ __global__ void __launch_bounds__(MESH_THREADS) mesh_chunks_kernel(ChunkArgs a) 
             }
             continue;
         }
-        // ---- stage 1: byte volume -> bit planes
+        // ---- stage 1: byte volume -> bit planes P[y][z] (bits x)
         const uint4 *src = reinterpret_cast<const uint4 *>(a.voxels + (size_t)chunk * VX_CHUNK_VOLUME);
         uint4 ra[4], rb[4];
 #pragma unroll
@@ -283,7 +311,12 @@ __global__ void __launch_bounds__(MESH_THREADS) mesh_chunks_kernel(ChunkArgs a) 
             ra[k] = ld_stream(src + 2 * r);
             rb[k] = ld_stream(src + 2 * r + 1);
         }
+        __syncthreads(); // the previous chunk's pool (aliases P0/P1) and counters are no longer read
         if (tid < 18) (&sm.faceRows[0])[tid] = 0; // faceRows, faceCols, faceSlices are contiguous
+        if (tid == 0) {
+            sm.pool_used = 0;
+            sm.slow = 0;
+        }
         load_halos(sm, a, chunk, tid);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -291,30 +324,31 @@ __global__ void __launch_bounds__(MESH_THREADS) mesh_chunks_kernel(ChunkArgs a) 
             uint32_t p0, p1;
             pack_row(ra[k], rb[k], p0, p1);
             const int y = r & 31, z = r >> 5;
-            sm.P0[y * PS + z] = p0;
-            sm.P1[y * PS + z] = p1;
+            sm.u.p.P0[y * PS + z] = p0;
+            sm.u.p.P1[y * PS + z] = p1;
         }
         __syncthreads();
 
-        // ---- stage 2a: +-X exposure, transposed into MX[sign][type][x][y] (bits z)
-        for (int item = warp; item < 64; item += MESH_WARPS) {
-            const int sign = item >> 5, y = item & 31; // lane = z
-            const uint32_t a0 = sm.P0[y * PS + lane], a1 = sm.P1[y * PS + lane];
-            const uint32_t S = a0 | a1;
-            const uint32_t hb = (sm.halo[sign][y] >> lane) & 1u;
-            const uint32_t nbS = sign == 0 ? ((S >> 1) | (hb << 31)) : ((S << 1) | hb);
-            uint32_t e[3];
-            exposure(a0, a1, nbS, e);
-#pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                const uint32_t col = __any_sync(FULL, e[t] != 0) ? transpose32(e[t], lane) : 0u; // lane = x, bits z
-                sm.MX[sign][t][lane * PS + y] = col;
+        // ---- stage 2: the two other orientations of the type planes, 128 warp transposes (empty ones skipped)
+        //      T[x][y] bits z  <-  for every y: rows z of P (bits x), transposed
+        //      R[z][x] bits y  <-  for every z: rows y of P (bits x), transposed
+        for (int item = warp; item < 128; item += MESH_WARPS) {
+            const int which = item >> 6, plane = (item >> 5) & 1, s = item & 31;
+            const uint32_t *P = plane ? sm.u.p.P1 : sm.u.p.P0;
+            if (which == 0) { // s = y, lane = z
+                uint32_t w = P[s * PS + lane];
+                if (__any_sync(FULL, w != 0)) w = transpose32(w, lane);
+                (plane ? sm.T1 : sm.T0)[lane * PS + s] = w; // lane = x
+            } else { // s = z, lane = y
+                uint32_t w = P[lane * PS + s];
+                if (__any_sync(FULL, w != 0)) w = transpose32(w, lane);
+                (plane ? sm.R1 : sm.R0)[s * PS + lane] = w; // lane = x
             }
         }
         __syncthreads();
 
-        // ---- pass 1: count
-        process_units<false>(sm, a, tid);
+        // ---- stage 3: greedy merge of every (face, slice) unit; quads go to the shared-memory pool
+        process_units<2>(sm, a, tid);
         __syncthreads();
         if (tid < 6) {
             uint32_t run = 0;
@@ -370,9 +404,20 @@ __global__ void __launch_bounds__(MESH_THREADS) mesh_chunks_kernel(ChunkArgs a) 
             }
         }
         __syncthreads();
-        // ---- pass 2: emit
-        if (sm.total && !sm.overflow) process_units<true>(sm, a, tid);
-        __syncthreads();
+        // ---- output in reference order (face, slice, block type, row, column)
+        if (sm.total && !sm.overflow) {
+            if (!sm.slow) { // pool -> quad stream, one warp per unit, 3 bytes per quad
+                for (int unit = warp; unit < 192; unit += MESH_WARPS) {
+                    const uint32_t n = sm.cnt[unit];
+                    if (!n) continue;
+                    const uint32_t *srcq = sm.u.pool + sm.pstart[unit];
+                    uint8_t *dst = a.quads + 3 * (size_t)(sm.base + sm.offs[unit]);
+                    for (uint32_t i = lane; i < 3 * n; i += 32) dst[i] = (uint8_t)(srcq[i / 3] >> (8 * (i % 3)));
+                }
+            } else {
+                process_units<1>(sm, a, tid); // rare: more quads than the pool holds
+            }
+        }
     }
 }
 
@@ -382,7 +427,7 @@ __global__ void greedy_slices_kernel(const uint32_t *masks, int n, VxQuad *out, 
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= n) return;
     const uint32_t d = masks[(size_t)w * 32 + lane];
-    const uint32_t c = greedy_warp<true>(d, lane, 0, nullptr, 0, out + (size_t)w * 512);
+    const uint32_t c = greedy_warp<1>(d, lane, 0, nullptr, 0, out + (size_t)w * 512, nullptr);
     if (lane == 0) n_out[w] = (int32_t)c;
 }
 
