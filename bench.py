@@ -43,6 +43,19 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` per launch from the newest committed ncu capture
+    (profiles/*_traffic.json, written from an `ncu --set full` run of tools/ncu_target.py), or None."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None
+    try:
+        return float(json.load(open(files[-1]))[kernel]["traffic"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -487,7 +500,7 @@ def run_cuda(args):
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": ("per step every rank renders its stripe (vx_render_frame_device), NCCL gather to GPU0, rank 0 copies the composed ARGB frame to page-locked host memory; wall clock between barriers, max over ranks" if world_size > 1 else "api.render_frame -> vx_render_frame, one synchronous call per frame: VP + camera + config in; the ARGB frame lands in page-locked host memory (written over PCIe by the raster kernel itself, no staging copy) together with the draw order; the call returns after the stream has drained")},
         "roofline": {"bound": "hbm", "kernel": knames[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic(knames[top]), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(top_bytes), "kernel_ms": float(kms[top]),
                      "kernel_share_of_step": float(kms[top] / kms.sum()) if kms.sum() > 0 else None},
         "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": threads, "kind": "port",

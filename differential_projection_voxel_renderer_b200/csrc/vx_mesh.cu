@@ -47,6 +47,7 @@ struct MeshSmem {
     uint32_t pstart[192];              // start of the unit's quads in the pool (fast path)
     uint32_t faceTot[6], faceBase[6];
     uint32_t faceRows[6], faceCols[6], faceSlices[6];
+    uint32_t occ[3]; // bit s: slice s along x / y / z holds a solid voxel
     uint32_t base, total, overflow, pool_used, slow;
 };
 
@@ -86,15 +87,16 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
     return x;
 }
 
-// TinyQuad::new (mesh.rs:283-307) as the three bytes b0 | b1 << 8 | b2 << 16
+// TinyQuad::new (mesh.rs:283-307) as the three bytes b0 | b1 << 8 | b2 << 16.  b0 = u | (v & 7) << 5,
+// b1 = v >> 3 | (w - 1) << 2, b2 = (h - 1) | type << 6: the two pieces of v are adjacent, so the 24-bit value is
+// simply u | v << 5 | (w - 1) << 10 | (h - 1) << 16 | type << 22.
 __device__ __forceinline__ uint32_t pack_tinyquad(uint32_t u, uint32_t v, uint32_t w, uint32_t h, uint32_t type) {
-    const uint32_t b0 = u | ((v & 7u) << 5);
-    const uint32_t b1 = (v >> 3) | ((w - 1u) << 2);
-    const uint32_t b2 = (h - 1u) | (type << 6);
-    return b0 | (b1 << 8) | (b2 << 16);
+    return u | (v << 5) | ((w - 1u) << 10) | ((h - 1u) << 16) | (type << 22);
 }
 
 // Greedy merge of one 32x32 mask (binary_greedy.rs:683-807).  Lane = row, d = that row's bits.  Returns the quad count.
+// One loop iteration per quad: the lowest row that still has bits is the reference's current row (rows are visited in
+// ascending order and a row is left only when it is empty), its lowest set bit starts the next run.
 //   MODE 0: count only.
 //   MODE 1: write TinyQuads (mesh.rs:283-307) of block type `type` to out[3*(pos + k)]; if out4 != nullptr write
 //           VxQuad {row, col, width, height} instead.
@@ -103,36 +105,32 @@ template <int MODE>
 __device__ __forceinline__ uint32_t greedy_warp(uint32_t d, int lane, uint32_t type, uint8_t *out, uint32_t pos,
                                                 VxQuad *out4, uint32_t *stage) {
     uint32_t n = 0;
-    uint32_t rows = __ballot_sync(FULL, d != 0);
-    while (rows) {
-        const int r = __ffs(rows) - 1;
-        rows &= rows - 1;
-        uint32_t cur = __shfl_sync(FULL, d, r);
-        while (cur) {
-            const int col = __ffs(cur) - 1;
-            const uint32_t run = ~(cur >> col);
-            const int h = run ? (__ffs(run) - 1) : 32; // trailing_ones
-            const uint32_t hmask = h >= 32 ? FULL : ((1u << h) - 1u);
-            const uint32_t m = hmask << col;
-            // rows below that still hold the whole run
-            const uint32_t ok = __ballot_sync(FULL, lane > r && (d & m) == m);
-            const uint32_t below = r == 31 ? 0u : (ok >> (r + 1));
-            const int ext = __ffs(~below) - 1; // consecutive rows r+1.. (bits >= 31-r are 0 -> terminates)
-            if (lane > r && lane <= r + ext) d &= ~m;
-            const uint32_t w = 1u + (uint32_t)ext;
-            if (MODE == 1) {
-                if (out4) {
-                    if (lane == 0) out4[pos + n] = VxQuad{(uint8_t)r, (uint8_t)col, (uint8_t)w, (uint8_t)h};
-                } else {
-                    const uint32_t packed = pack_tinyquad((uint32_t)r, (uint32_t)col, w, (uint32_t)h, type);
-                    if (lane < 3) out[3 * (size_t)(pos + n) + lane] = (uint8_t)(packed >> (8 * lane));
-                }
-            } else if (MODE == 2) {
-                if (lane == 0 && pos + n < (uint32_t)STAGE_CAP) stage[pos + n] = pack_tinyquad((uint32_t)r, (uint32_t)col, w, (uint32_t)h, type);
+    for (;;) {
+        const uint32_t rows = __ballot_sync(FULL, d != 0);
+        if (!rows) break;
+        const int r = __clz(__brev(rows)); // lowest row with bits (rows != 0)
+        const uint32_t cur = __shfl_sync(FULL, d, r);
+        const int col = __clz(__brev(cur));
+        // the run of ones that starts at the lowest set bit: adding that bit carries through the run
+        const uint32_t m = cur & ~(cur + (cur & (0u - cur)));
+        const int h = __popc(m); // trailing_ones of (cur >> col)
+        // rows below that still hold the whole run
+        const uint32_t ok = __ballot_sync(FULL, lane > r && (d & m) == m);
+        const uint32_t below = r == 31 ? 0u : (ok >> (r + 1));
+        const int ext = __clz(__brev(~below)); // consecutive rows r+1.. (bits >= 31-r of ~below are 1 -> ext <= 31-r)
+        if ((uint32_t)(lane - r) <= (uint32_t)ext) d &= ~m;
+        const uint32_t w = 1u + (uint32_t)ext;
+        if (MODE == 1) {
+            if (out4) {
+                if (lane == 0) out4[pos + n] = VxQuad{(uint8_t)r, (uint8_t)col, (uint8_t)w, (uint8_t)h};
+            } else {
+                const uint32_t packed = pack_tinyquad((uint32_t)r, (uint32_t)col, w, (uint32_t)h, type);
+                if (lane < 3) out[3 * (size_t)(pos + n) + lane] = (uint8_t)(packed >> (8 * lane));
             }
-            n++;
-            cur &= ~m;
+        } else if (MODE == 2) {
+            if (lane == 0 && pos + n < (uint32_t)STAGE_CAP) stage[pos + n] = pack_tinyquad((uint32_t)r, (uint32_t)col, w, (uint32_t)h, type);
         }
+        n++;
     }
     return n;
 }
@@ -241,18 +239,25 @@ __device__ __forceinline__ void process_units(MeshSmem &sm, const ChunkArgs &a, 
     const int lane = tid & 31, warp = tid >> 5;
     for (int unit = warp; unit < 192; unit += MESH_WARPS) {
         const int face = unit >> 5, slice = unit & 31;
+        if (MODE == 2) {
+            // a slice without a solid voxel has no faces: skip it without touching the planes
+            if (!((sm.occ[face >> 1] >> slice) & 1u)) {
+                if (lane == 0) sm.cnt[unit] = 0;
+                continue;
+            }
+        }
         uint32_t d[3];
         unit_rows(sm, face, slice, lane, d);
         if (MODE == 2) {
-            uint32_t n = 0, rowsAny = 0, colsAny = 0;
+            uint32_t n = 0, colsAny = 0;
+            const uint32_t rowsAny = __ballot_sync(FULL, (d[0] | d[1] | d[2]) != 0);
+            if (rowsAny) {
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                const uint32_t any = __ballot_sync(FULL, d[t] != 0);
-                if (any) {
-                    rowsAny |= any;
-                    colsAny |= __reduce_or_sync(FULL, d[t]);
+                for (int t = 0; t < 3; ++t) {
+                    colsAny |= d[t];
                     n += greedy_warp<2>(d[t], lane, (uint32_t)(t + 1), nullptr, n, nullptr, sm.stage[warp]);
                 }
+                colsAny = __reduce_or_sync(FULL, colsAny);
             }
             uint32_t start = 0;
             if (lane == 0) {
@@ -316,6 +321,7 @@ __global__ void __launch_bounds__(MESH_THREADS, 5) mesh_chunks_kernel(ChunkArgs 
         if (tid == 0) {
             sm.pool_used = 0;
             sm.slow = 0;
+            sm.occ[0] = sm.occ[1] = sm.occ[2] = 0;
         }
         load_halos(sm, a, chunk, tid);
 #pragma unroll
@@ -337,11 +343,21 @@ __global__ void __launch_bounds__(MESH_THREADS, 5) mesh_chunks_kernel(ChunkArgs 
             const uint32_t *P = plane ? sm.u.p.P1 : sm.u.p.P0;
             if (which == 0) { // s = y, lane = z
                 uint32_t w = P[s * PS + lane];
-                if (__any_sync(FULL, w != 0)) w = transpose32(w, lane);
+                const uint32_t xs = __reduce_or_sync(FULL, w); // x columns present in slice y
+                if (xs) {
+                    w = transpose32(w, lane);
+                    if (lane == 0) {
+                        atomicOr(&sm.occ[1], 1u << s);
+                        atomicOr(&sm.occ[0], xs);
+                    }
+                }
                 (plane ? sm.T1 : sm.T0)[lane * PS + s] = w; // lane = x
             } else { // s = z, lane = y
                 uint32_t w = P[lane * PS + s];
-                if (__any_sync(FULL, w != 0)) w = transpose32(w, lane);
+                if (__any_sync(FULL, w != 0)) {
+                    w = transpose32(w, lane);
+                    if (lane == 0) atomicOr(&sm.occ[2], 1u << s);
+                }
                 (plane ? sm.R1 : sm.R0)[s * PS + lane] = w; // lane = x
             }
         }
