@@ -316,3 +316,40 @@ def test_mapped_host_framebuffer_is_written_in_place(ctx, ob, scene5):
     color[...] = 0
     c, d, _ = api.render_frame(batch, vp, cam.position, cfg, mesh_ids=ids, color_out=color, ctx=ctx)
     assert np.array_equal(color, oc) and np.array_equal(d.view(np.uint32), od.view(np.uint32))
+
+
+def test_full_size_frame_3840x2160_vd32_and_its_eight_stripes(ctx, ob):
+    """BASELINE cfg 5: 3840x2160, view distance 32 (137,065 lattice chunks, ~5.9 k Varied), camera (0,10,20); the full
+    frame and the eight 270-row stripes of the multi-GPU raster split, all bit-identical to the oracle."""
+    pos, world, p, v, nb = vx_scenes.terrain_scene(32)
+    assert pos.shape[0] == 137065
+    batch = api.BinaryGreedyMesher.mesh_batch(v, p, nb, None, ctx)
+    ref = ob.mesh_chunks(v, nb, None, p)
+    got = batch.download()
+    assert np.array_equal(got["quad_count"], ref.quad_count)
+    assert np.array_equal(got["slice_offsets"], ref.slice_offsets) and np.array_equal(got["face_aabb"], ref.face_aabb)
+    for i in range(0, p.shape[0], 97):
+        assert np.array_equal(batch.chunk_quads(i).reshape(-1), ref.chunk_quads(i).reshape(-1))
+    w, h, vd = 3840, 2160, 32
+    cam = vx_scenes.main_camera(w, h)
+    vp, ids, oc, od, osurv = oracle_frame(ob, ref, p, cam, w, h, vd, threads=8)
+    vis_all = api.get_visible_chunks_frustum(pos, cam.position, vp, vd, True, ctx)
+    assert np.array_equal(vis_all, ob.cull_chunks(pos, vp, cam.position, vd))
+    cfg = api.default_frame_config(w, h)
+    color, depth, surv = api.render_frame(batch, vp, cam.position, cfg, mesh_ids=None, view_distance=vd, ctx=ctx)
+    assert np.array_equal(surv, osurv)
+    assert np.array_equal(depth.view(np.uint32), od.view(np.uint32))
+    assert np.array_equal(color, oc)
+    st = api.frame_stats(ctx)
+    print("4K vd32: survivors", st.n_survivors, "quads", st.n_quads, "triangles", st.n_triangles, "bin entries", st.n_bin_entries,
+          "max bin", st.reserved[0], "work items", st.reserved[1])
+    from differential_projection_voxel_renderer_b200 import sharding
+    parts = []
+    for g in range(8):
+        c8 = api.default_frame_config(w, h)
+        c8.stripe_y0, c8.stripe_rows = sharding.stripe_of(h, g, 8)
+        assert c8.stripe_rows == 270
+        c, d, _ = api.render_frame(batch, vp, cam.position, c8, mesh_ids=None, view_distance=vd, want_depth=False, ctx=ctx)
+        parts.append(c)
+    assert np.array_equal(np.concatenate(parts), oc)
+    batch.release()

@@ -7,7 +7,9 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import vx_scenes
 from differential_projection_voxel_renderer_b200 import api
-W, H, VD = 1280, 720, 12
+W = int(sys.argv[1]) if len(sys.argv) > 1 else 1280
+H = int(sys.argv[2]) if len(sys.argv) > 2 else 720
+VD = int(sys.argv[3]) if len(sys.argv) > 3 else 12
 pos, world, p, v, nb = vx_scenes.terrain_scene(VD)
 cam = vx_scenes.main_camera(W, H)
 ctx = api.Context(0)
@@ -35,4 +37,4 @@ for _ in range(20):
     with torch.cuda.stream(stream):
         flush.fill_(1)
     api.render_frame_device(batch, vp, cam.position, cfgp, VD, ctx); ks += api.frame_kernel_times(ctx)
-print(os.environ.get("VX_B200_LIB", "default"), "frame ms mean %.4f median %.4f min %.4f | kernels us" % (ms.mean(), np.median(ms), ms.min()), np.round(ks / 20 * 1000, 1))
+print(os.environ.get("VX_B200_LIB", "default"), f"{W}x{H} vd{VD}", "frame ms mean %.4f median %.4f min %.4f | kernels us" % (ms.mean(), np.median(ms), ms.min()), np.round(ks / 20 * 1000, 1))
