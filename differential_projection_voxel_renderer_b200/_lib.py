@@ -84,6 +84,7 @@ PROTOTYPES = {
     "vx_mesh_batch_release": (None, [_P, _P]),
     "vx_greedy_mesh_slices": (C.c_int, [_P, _P, _I, _P, _P]),
     "vx_cull_chunks": (C.c_int, [_P, _P, _I, _P, _P, _I, _I, _P]),
+    "vx_horizon_cull": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, C.c_float, C.c_float, C.c_float, C.POINTER(_I)]),
     "vx_default_frame_config": (None, [C.POINTER(VxFrameConfig), _I, _I]),
     "vx_default_atlas": (None, [C.POINTER(VxAtlas)]),
     "vx_set_atlas": (C.c_int, [_P, C.POINTER(VxAtlas)]),

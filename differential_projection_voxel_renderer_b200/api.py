@@ -319,6 +319,20 @@ def get_visible_chunks_frustum(positions, camera_position, view_projection, view
     return out
 
 
+def apply_horizon_culling(camera_position, centers, order=None, bins: int = 128, base_margin: float = 0.1,
+                          margin_dist_factor: float = 0.05, min_dist_chunks: float = 2.0, ctx: Optional[Context] = None) -> np.ndarray:
+    """culling::apply_horizon_culling (culling.rs:40-119): centers (N,3) VisibleMesh centres, order = candidate ids
+    (default: all).  Returns the kept ids, stably sorted front to back."""
+    ctx = ctx or default_context()
+    centers = np.ascontiguousarray(centers, dtype=np.float32).reshape(-1, 3)
+    cam = np.ascontiguousarray(camera_position, dtype=np.float32).reshape(3)
+    order = np.arange(centers.shape[0], dtype=np.int32) if order is None else np.ascontiguousarray(order, dtype=np.int32).copy()
+    nk = C.c_int32(0)
+    ctx.check(ctx.lib.vx_horizon_cull(ctx.handle, _p(cam), _p(centers), centers.shape[0], _p(order), order.shape[0], int(bins),
+                                      float(base_margin), float(margin_dist_factor), float(min_dist_chunks), C.byref(nk)))
+    return order[:nk.value].copy()
+
+
 class Framebuffer:
     """framebuffer.rs:197-245: ARGB colour + f32 depth, row-major."""
 

@@ -2,6 +2,8 @@
 // packet projection (the reference's "Hyper-Pipeline" projection stage), legacy vertex transform and a
 // vertex dump used by the parity tests.                      (compiled with -fmad=false, see vx_math.cuh)
 #include "vx_common.cuh"
+
+#include <math_constants.h>
 #include "vx_math.cuh"
 
 namespace {
@@ -142,6 +144,122 @@ VxMat4 to_mat(const float vp[16]) {
     return m;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// culling::apply_horizon_culling (culling.rs:40-119).  One CTA.  The reference is a serial front-to-back sweep with a
+// running horizon per angular bin; bins are independent, so after the stable distance sort every bin is swept by its
+// own thread.  atan2 is evaluated in f64 and rounded to f32 (the reference calls the platform libm's atan2f; results
+// can differ from it only for meshes whose angle falls within an ulp of a bin boundary -- DESIGN.md 8).
+// ------------------------------------------------------------------------------------------------
+constexpr int HZ_THREADS = 1024;
+
+struct HorizonArgs {
+    const float *centers; // [*][3]
+    int32_t *order;       // [n] in: candidate ids, out: kept ids front-to-back
+    int32_t n, bins;
+    float cam[3];
+    float base_margin, margin_dist_factor, min_dist_chunks;
+    float *key;           // [n] scratch: distance_sq in input order
+    int32_t *sorted;      // [n] scratch: ids sorted by distance
+    int32_t *bin_of;      // [n] scratch: bin of sorted[i], -1 = always kept
+    float *slope, *margin, *top; // [n] scratch
+    uint8_t *keep;        // [n] scratch
+    int32_t *n_kept;
+};
+
+__global__ void __launch_bounds__(HZ_THREADS) horizon_cull_kernel(HorizonArgs a) {
+    __shared__ uint32_t warp_sums[HZ_THREADS / 32];
+    __shared__ uint32_t s_run;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // distance_sq of every candidate (main.rs:286-290 form: |center - cam|^2, left to right)
+    for (int i = tid; i < a.n; i += HZ_THREADS) {
+        const float *c = a.centers + 3 * (size_t)a.order[i];
+        const float dx = c[0] - a.cam[0], dy = c[1] - a.cam[1], dz = c[2] - a.cam[2];
+        a.key[i] = dx * dx + dy * dy + dz * dz;
+    }
+    __syncthreads();
+    // stable sort by distance_sq (partial_cmp, ties keep input order): rank = elements ordered before mine
+    for (int i = tid; i < a.n; i += HZ_THREADS) {
+        const float k = a.key[i];
+        int rank = 0;
+        for (int j = 0; j < a.n; ++j) {
+            const float kj = a.key[j];
+            rank += (kj < k || (kj == k && j < i)) ? 1 : 0;
+        }
+        a.sorted[rank] = a.order[i];
+    }
+    __syncthreads();
+    // per-mesh quantities
+    const float chunk_size = (float)VX_CHUNK_SIZE, half_chunk = chunk_size * 0.5f;
+    const float PI = 3.14159265358979323846f;
+    for (int i = tid; i < a.n; i += HZ_THREADS) {
+        const float *c = a.centers + 3 * (size_t)a.sorted[i];
+        const float tx = c[0] - a.cam[0], tz = c[2] - a.cam[2];
+        const float dist_xz = sqrtf(tx * tx + tz * tz);
+        int32_t bin = -1;
+        float slope = 0.0f, margin = 0.0f, top = 0.0f;
+        if (!(dist_xz < 1e-3f)) {
+            const float dist_chunks = dist_xz / chunk_size;
+            if (!(dist_chunks < a.min_dist_chunks)) {
+                const float angle = (float)atan2((double)tz, (double)tx);
+                const float bin_f = (angle + PI) / (2.0f * PI) * (float)a.bins;
+                long b = (long)vx_f2i(floorf(bin_f));
+                if (b < 0) b += a.bins;
+                bin = (int32_t)(b % a.bins);
+                slope = (c[1] - a.cam[1]) / dist_xz;
+                margin = a.base_margin * (1.0f + dist_chunks * a.margin_dist_factor);
+                top = (c[1] + half_chunk - a.cam[1]) / dist_xz;
+            }
+        }
+        a.bin_of[i] = bin;
+        a.slope[i] = slope;
+        a.margin[i] = margin;
+        a.top[i] = top;
+        a.keep[i] = bin < 0 ? 1 : 0;
+    }
+    __syncthreads();
+    // one thread per angular bin sweeps the sorted list with its running horizon
+    for (int b = tid; b < a.bins; b += HZ_THREADS) {
+        float horizon = -CUDART_INF_F;
+        for (int i = 0; i < a.n; ++i) {
+            if (a.bin_of[i] != b) continue;
+            const float s = a.slope[i];
+            const bool cull = s >= 0.0f && (s + a.margin[i]) < horizon;
+            if (!cull) {
+                a.keep[i] = 1;
+                if (a.top[i] > horizon) horizon = a.top[i];
+            }
+        }
+    }
+    __syncthreads();
+    // stable compaction of the kept meshes
+    if (tid == 0) s_run = 0;
+    __syncthreads();
+    for (int base = 0; base < a.n; base += HZ_THREADS) {
+        const int i = base + tid;
+        const uint32_t k = (i < a.n && a.keep[i]) ? 1u : 0u;
+        uint32_t inc = k;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (int w = 0; w < HZ_THREADS / 32; ++w) {
+            const uint32_t c = warp_sums[w];
+            if (w < warp) before += c;
+            total += c;
+        }
+        if (k) a.order[s_run + before + inc - 1] = a.sorted[i];
+        __syncthreads();
+        if (tid == 0) s_run += total;
+        __syncthreads();
+    }
+    if (tid == 0) *a.n_kept = (int32_t)s_run;
+}
+
 // vx_div_fast vs the `/` operator on pseudo-random operand pairs.  counters: [0] mismatching quotients among pairs the
 // guard accepted, [1] pairs the guard sent to the fallback, [2] pairs tested.
 __global__ void selftest_division_kernel(unsigned long long seed, unsigned long long n, int mode, unsigned long long *counters) {
@@ -187,6 +305,50 @@ __global__ void selftest_division_kernel(unsigned long long seed, unsigned long 
 } // namespace
 
 extern "C" {
+
+int vx_horizon_cull(VxContext *ctx, const float cam_pos[3], const float *centers, int32_t n_centers, int32_t *order_inout,
+                    int32_t n, int32_t bins, float base_margin, float margin_dist_factor, float min_dist_chunks,
+                    int32_t *n_kept) {
+    if (!ctx || !cam_pos || !n_kept || n < 0 || n_centers < 0 || bins <= 0 || (n > 0 && (!centers || !order_inout)))
+        return vx_fail(ctx, VX_ERR_INVALID, "vx_horizon_cull: bad argument");
+    *n_kept = 0;
+    if (n == 0) return VX_OK;
+    if (n > (1 << 16)) return vx_fail(ctx, VX_ERR_CAPACITY, "vx_horizon_cull: more than 65536 meshes");
+    for (int32_t i = 0; i < n; ++i)
+        if (order_inout[i] < 0 || order_inout[i] >= n_centers) return vx_fail(ctx, VX_ERR_INVALID, "vx_horizon_cull: mesh id out of range");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nn = (size_t)n;
+    // scratch: centers | order | key | sorted | bin_of | slope | margin | top | keep | n_kept
+    const size_t off_order = sizeof(float) * 3 * (size_t)n_centers;
+    const size_t off_key = off_order + 4 * nn, off_sorted = off_key + 4 * nn, off_bin = off_sorted + 4 * nn;
+    const size_t off_slope = off_bin + 4 * nn, off_margin = off_slope + 4 * nn, off_top = off_margin + 4 * nn;
+    const size_t off_keep = off_top + 4 * nn, off_cnt = (off_keep + nn + 15) & ~(size_t)15;
+    VX_CUDA(ctx, ctx->tmp_a.reserve(off_cnt + 16));
+    uint8_t *base = ctx->tmp_a.as<uint8_t>();
+    VX_CUDA(ctx, cudaMemcpyAsync(base, centers, off_order, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(base + off_order, order_inout, 4 * nn, cudaMemcpyHostToDevice, ctx->stream));
+    HorizonArgs a;
+    a.centers = reinterpret_cast<const float *>(base);
+    a.order = reinterpret_cast<int32_t *>(base + off_order);
+    a.n = n;
+    a.bins = bins;
+    a.cam[0] = cam_pos[0]; a.cam[1] = cam_pos[1]; a.cam[2] = cam_pos[2];
+    a.base_margin = base_margin; a.margin_dist_factor = margin_dist_factor; a.min_dist_chunks = min_dist_chunks;
+    a.key = reinterpret_cast<float *>(base + off_key);
+    a.sorted = reinterpret_cast<int32_t *>(base + off_sorted);
+    a.bin_of = reinterpret_cast<int32_t *>(base + off_bin);
+    a.slope = reinterpret_cast<float *>(base + off_slope);
+    a.margin = reinterpret_cast<float *>(base + off_margin);
+    a.top = reinterpret_cast<float *>(base + off_top);
+    a.keep = base + off_keep;
+    a.n_kept = reinterpret_cast<int32_t *>(base + off_cnt);
+    horizon_cull_kernel<<<1, HZ_THREADS, 0, ctx->stream>>>(a);
+    VX_CHECK_LAUNCH(ctx);
+    VX_CUDA(ctx, cudaMemcpyAsync(n_kept, a.n_kept, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(order_inout, a.order, 4 * nn, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
 
 int vx_selftest_division(VxContext *ctx, uint64_t seed, uint64_t n_pairs, int32_t mode, uint64_t counters_out[3]) {
     if (!ctx || !counters_out) return vx_fail(ctx, VX_ERR_INVALID, "vx_selftest_division: bad argument");

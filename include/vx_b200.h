@@ -194,6 +194,15 @@ VX_API int vx_greedy_mesh_slices(VxContext *ctx, const uint32_t *masks, int32_t 
 VX_API int vx_cull_chunks(VxContext *ctx, const int32_t *positions, int32_t n, const float vp[16], const float cam_pos[3],
                    int32_t view_distance, int32_t frustum_culling, uint8_t *visible_out);
 
+/* culling::apply_horizon_culling (culling.rs:40-119) with HorizonCullingConfig (:16-36; defaults bins 128,
+ * base_margin 0.1, margin_dist_factor 0.05, min_dist_chunks 2.0).  centers: n_centers x 3 VisibleMesh centres
+ * (main.rs:286-290); order_inout: n mesh ids -> the kept ids, stably sorted front to back; *n_kept of them.
+ * Optional stage: main.rs does not call it (:368-377).  atan2 is evaluated in f64 and rounded (the reference uses the
+ * platform libm): a mesh within an ulp of a bin boundary may land in the neighbouring bin. */
+VX_API int vx_horizon_cull(VxContext *ctx, const float cam_pos[3], const float *centers, int32_t n_centers, int32_t *order_inout,
+                    int32_t n, int32_t bins, float base_margin, float margin_dist_factor, float min_dist_chunks,
+                    int32_t *n_kept);
+
 /* ---- rendering -------------------------------------------------------- */
 
 VX_API void vx_default_frame_config(VxFrameConfig *cfg, int32_t width, int32_t height);
