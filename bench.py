@@ -176,8 +176,10 @@ def run_reference(args):
     out = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
         "ms_per_step": 1000.0 * el / n, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": "full frame 1280x720 view distance 12 (cull+project+raster, meshes cached)",
-                                         "chunks": int(pos.shape[0]), "varied_chunks": int(p.shape[0])},
+        "data": "synthetic", "config": {"workload": "full frame 1280x720 view distance 12 (filter A + filter B/sort + project/clip/cull + span raster), "
+                                                     "meshes cached; BASELINE.json configs[2]",
+                                         "chunks": int(pos.shape[0]), "varied_chunks": int(p.shape[0]),
+                                         "camera": "(0,10,20) yaw 0 pitch 0 fov 70", "parallelism": f"{threads} host threads (stripes)"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{n} full frames; C restatement of the reference CPU path (oracle/), stripe-parallel over all host threads; "
                                    "the Rust reference itself cannot be built in this image (no cargo/rustc)"},
@@ -190,6 +192,18 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------------------------------
+def finish_distributed(dist):
+    """All ranks leave together: barrier, tear the process group down, and exit without running interpreter-exit
+    destructors (torch's NCCL watchdog otherwise races the CUDA context teardown and aborts the process)."""
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    finally:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def run_cuda(args):
     import torch
     from differential_projection_voxel_renderer_b200 import api
@@ -198,10 +212,13 @@ def run_cuda(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     dist = None
+    # NCCL writes its banner / debug lines to stdout by default: the contract is ONE JSON line there
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world_size > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
@@ -285,8 +302,8 @@ def run_cuda(args):
     # keep the same load running until the sampler has seen >= 1.5 s of it (the timed frames are ~tens of microseconds)
     t_probe = time.perf_counter()
     while time.perf_counter() - t_probe < 1.5:
-        for _ in range(50):
-            step_device()
+        for _ in range(50):  # this rank's frames only: a time-based loop must not contain collectives (ranks would disagree on the count)
+            api.render_frame_device(batch, vp, cam.position, cfg_async, VD, ctx)
         ctx.synchronize()
     clocks = sampler.stop()
     if dist is not None:
@@ -371,9 +388,7 @@ def run_cuda(args):
         e2e_multi = ne2e / float(el.item())
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
+        return finish_distributed(dist)  # waits for rank 0 (which still has the single-rank sections to run)
 
     # ---- warm-L2 back-to-back throughput (how the path is used in a render loop) --------------------------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -523,9 +538,9 @@ def run_cuda(args):
     }
     print(json.dumps(out), flush=True)
     batch.release()
-    ctx.close()
     if dist is not None:
-        dist.destroy_process_group()
+        return finish_distributed(dist)
+    ctx.close()
     return 0
 
 
