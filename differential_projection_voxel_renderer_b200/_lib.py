@@ -74,6 +74,7 @@ PROTOTYPES = {
     "vx_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "vx_host_free": (None, [_P, _P]),
     "vx_mesh_chunks": (C.c_int, [_P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
+    "vx_mesh_batch_update": (C.c_int, [_P, _P, _P, _I, _P, _P, C.POINTER(_I)]),
     "vx_mesh_chunks_device": (C.c_int, [_P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
     "vx_mesh_chunk_subset_device": (C.c_int, [_P, _P, _P, _P, _P, _I, _P, _I, C.POINTER(_P)]),
     "vx_remesh_chunks_device": (C.c_int, [_P, _P, _P, _P, _P]),

@@ -194,6 +194,17 @@ class MeshBatch:
             return None
         return ChunkMesh(position, self.chunk_quads(i), h["slice_offsets"][i], h["face_aabb"][i])
 
+    def update(self, chunk_ids, voxels, uniform_flags=None) -> int:
+        """Re-mesh edited chunks (and the six neighbours of each, main.rs:225-280) in place: vx_mesh_batch_update.
+        voxels: (len(chunk_ids), 32768) new data.  Returns the number of chunks re-meshed."""
+        ids = np.ascontiguousarray(chunk_ids, dtype=np.int32).reshape(-1)
+        vox = np.ascontiguousarray(voxels, dtype=np.uint8).reshape(ids.shape[0], CHUNK_VOLUME)
+        uf = None if uniform_flags is None else np.ascontiguousarray(uniform_flags, dtype=np.uint8).reshape(ids.shape[0])
+        n = C.c_int32(0)
+        self.ctx.check(self.ctx.lib.vx_mesh_batch_update(self.ctx.handle, self.handle, _p(ids), ids.shape[0], _p(vox), _p(uf), C.byref(n)))
+        self._host = None
+        return int(n.value)
+
     def release(self):
         if self.handle:
             self.ctx.lib.vx_mesh_batch_release(self.ctx.handle, self.handle)

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/vx_b200.h"
 
@@ -60,7 +61,12 @@ struct VxMeshBatch {
     int64_t total_quads = -1; // -1 until read back
     int32_t n_meshes = -1;
     VxDeviceBuffer quads, quad_base, quad_count, slice_offsets, face_aabb, has_mesh, positions;
-    VxDeviceBuffer cursor; // 2 x unsigned long long: quad cursor, mesh counter
+    VxDeviceBuffer cursor; // 4 x unsigned long long: quad cursor, mesh counter, overflow flag, spare
+    // world copy owned by the batch (host-array entry points only): lets vx_mesh_batch_update re-mesh edited chunks
+    // and their neighbours without re-uploading the world
+    VxDeviceBuffer world_voxels, world_neighbors, world_flags, update_ids;
+    bool owns_world = false, has_neighbors = false, has_flags = false;
+    std::vector<int32_t> host_neighbors; // [n][6] host copy for the neighbour invalidation list
 };
 
 struct VxFrameScratch;

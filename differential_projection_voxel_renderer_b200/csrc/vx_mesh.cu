@@ -141,7 +141,8 @@ struct ChunkArgs {
     const uint8_t *uniform_flags;
     int32_t n_chunks;       // chunks in the voxel / neighbour arrays (what neighbour indices refer to)
     const int32_t *subset;  // chunk ids to mesh (a shard of the world), or null = all n_chunks
-    int32_t n_out;          // chunks meshed = entries of the output arrays
+    int32_t n_out;          // chunks meshed
+    int32_t out_by_chunk;   // 1: per-chunk outputs are written at the chunk's own index (in-place update of a batch)
     uint8_t *quads;
     unsigned long long cap_quads;
     uint32_t *quad_base, *quad_count, *slice_offsets;
@@ -294,16 +295,17 @@ __global__ void __launch_bounds__(MESH_THREADS, 5) mesh_chunks_kernel(ChunkArgs 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int oi = blockIdx.x; oi < a.n_out; oi += gridDim.x) {
-        const int chunk = a.subset ? a.subset[oi] : oi; // input chunk; outputs are indexed by oi
-        uint32_t *so = a.slice_offsets + (size_t)oi * 198;
-        int32_t *ab = a.face_aabb + (size_t)oi * 36;
+        const int chunk = a.subset ? a.subset[oi] : oi; // input chunk
+        const int oo = a.out_by_chunk ? chunk : oi;     // where its outputs go
+        uint32_t *so = a.slice_offsets + (size_t)oo * 198;
+        int32_t *ab = a.face_aabb + (size_t)oo * 36;
         if (a.uniform_flags && a.uniform_flags[chunk]) { // Uniform chunk -> None (binary_greedy.rs:87)
             for (int i = tid; i < 198; i += MESH_THREADS) so[i] = 0;
             if (tid < 36) ab[tid] = (tid % 6) < 3 ? 32 : 0;
             if (tid == 0) {
-                a.quad_base[oi] = 0;
-                a.quad_count[oi] = 0;
-                a.has_mesh[oi] = 0;
+                a.quad_base[oo] = 0;
+                a.quad_count[oo] = 0;
+                a.has_mesh[oo] = 0;
             }
             continue;
         }
@@ -390,9 +392,9 @@ __global__ void __launch_bounds__(MESH_THREADS, 5) mesh_chunks_kernel(ChunkArgs 
             sm.overflow = (base + run > a.cap_quads) ? 1u : 0u;
             if (sm.overflow) atomicExch(a.cursor + 2, 1ull);
             sm.base = (uint32_t)base;
-            a.quad_base[oi] = (uint32_t)base;
-            a.quad_count[oi] = run;
-            a.has_mesh[oi] = run ? 1 : 0; // mesh.is_empty() -> None (binary_greedy.rs:116-120)
+            a.quad_base[oo] = (uint32_t)base;
+            a.quad_count[oo] = run;
+            a.has_mesh[oo] = run ? 1 : 0; // mesh.is_empty() -> None (binary_greedy.rs:116-120)
         }
         __syncthreads();
         if (tid < 192) {
@@ -461,17 +463,21 @@ int batch_alloc(VxContext *ctx, VxMeshBatch *b, int32_t n, int64_t cap_quads) {
     return VX_OK;
 }
 
+// append = true: in-place update of the chunks in d_subset (n_sub of them): outputs at the chunks' own indices, new
+// quads appended behind the current end of the quad stream (the old ones become dead space).
 int run_mesher(VxContext *ctx, const uint8_t *d_vox, const int32_t *d_nb, const uint8_t *d_uf, VxMeshBatch *b,
-               bool allow_regrow, const int32_t *d_subset = nullptr, int32_t n_total = -1) {
+               bool allow_regrow, const int32_t *d_subset = nullptr, int32_t n_total = -1, bool append = false,
+               int32_t n_sub = 0) {
     for (int attempt = 0; attempt < 2; ++attempt) {
-        VX_CUDA(ctx, cudaMemsetAsync(b->cursor.ptr, 0, sizeof(unsigned long long) * 4, ctx->stream));
+        if (!append) VX_CUDA(ctx, cudaMemsetAsync(b->cursor.ptr, 0, sizeof(unsigned long long) * 4, ctx->stream));
         ChunkArgs a;
         a.voxels = d_vox;
         a.neighbors = d_nb;
         a.uniform_flags = d_uf;
         a.n_chunks = n_total >= 0 ? n_total : b->n_chunks;
         a.subset = d_subset;
-        a.n_out = b->n_chunks;
+        a.n_out = append ? n_sub : b->n_chunks;
+        a.out_by_chunk = append ? 1 : 0;
         a.quads = b->quads.as<uint8_t>();
         a.cap_quads = (unsigned long long)b->cap_quads;
         a.quad_base = b->quad_base.as<uint32_t>();
@@ -484,12 +490,13 @@ int run_mesher(VxContext *ctx, const uint8_t *d_vox, const int32_t *d_nb, const 
         VX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mesh_chunks_kernel, MESH_THREADS, 0));
         if (per_sm < 1) per_sm = 1;
         int grid = ctx->num_sms * per_sm;
-        if (grid > b->n_chunks) grid = b->n_chunks;
+        if (grid > a.n_out) grid = a.n_out;
+        if (grid < 1) grid = 1;
         mesh_chunks_kernel<<<grid, MESH_THREADS, 0, ctx->stream>>>(a);
         VX_CHECK_LAUNCH(ctx);
         b->total_quads = -1;
         b->n_meshes = -1;
-        if (!allow_regrow) return VX_OK;
+        if (!allow_regrow || append) return VX_OK;
         unsigned long long h[4];
         VX_CUDA(ctx, cudaMemcpyAsync(h, b->cursor.ptr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -595,17 +602,96 @@ int vx_mesh_chunks(VxContext *ctx, const uint8_t *voxels, const int32_t *positio
     if (!ctx || !out || n_chunks < 0 || (n_chunks > 0 && !voxels)) return vx_fail(ctx, VX_ERR_INVALID, "vx_mesh_chunks: bad argument");
     VX_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t n = (size_t)n_chunks;
-    VX_CUDA(ctx, ctx->tmp_a.reserve(n * VX_CHUNK_VOLUME + 16));
-    VX_CUDA(ctx, ctx->tmp_b.reserve(n * 6 * sizeof(int32_t) + 16));
-    VX_CUDA(ctx, ctx->tmp_c.reserve(n + 16));
+    // the world copy stays with the batch (vx_mesh_batch_update edits it in place)
+    VxDeviceBuffer wv, wn, wf;
+    VX_CUDA(ctx, wv.reserve(n * VX_CHUNK_VOLUME + 16));
+    VX_CUDA(ctx, wn.reserve(n * 6 * sizeof(int32_t) + 16));
+    VX_CUDA(ctx, wf.reserve(n + 16));
     VX_CUDA(ctx, ctx->tmp_d.reserve(n * 3 * sizeof(int32_t) + 16));
-    if (n) VX_CUDA(ctx, cudaMemcpyAsync(ctx->tmp_a.ptr, voxels, n * VX_CHUNK_VOLUME, cudaMemcpyHostToDevice, ctx->stream));
-    if (n && neighbors) VX_CUDA(ctx, cudaMemcpyAsync(ctx->tmp_b.ptr, neighbors, n * 6 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    if (n && uniform_flags) VX_CUDA(ctx, cudaMemcpyAsync(ctx->tmp_c.ptr, uniform_flags, n, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) VX_CUDA(ctx, cudaMemcpyAsync(wv.ptr, voxels, n * VX_CHUNK_VOLUME, cudaMemcpyHostToDevice, ctx->stream));
+    if (n && neighbors) VX_CUDA(ctx, cudaMemcpyAsync(wn.ptr, neighbors, n * 6 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (n && uniform_flags) VX_CUDA(ctx, cudaMemcpyAsync(wf.ptr, uniform_flags, n, cudaMemcpyHostToDevice, ctx->stream));
+    else if (n) VX_CUDA(ctx, cudaMemsetAsync(wf.ptr, 0, n, ctx->stream));
     if (n && positions) VX_CUDA(ctx, cudaMemcpyAsync(ctx->tmp_d.ptr, positions, n * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    return vx_mesh_chunks_device(ctx, ctx->tmp_a.as<uint8_t>(), positions ? ctx->tmp_d.as<int32_t>() : nullptr,
-                                 neighbors ? ctx->tmp_b.as<int32_t>() : nullptr,
-                                 uniform_flags ? ctx->tmp_c.as<uint8_t>() : nullptr, n_chunks, out);
+    int rc = vx_mesh_chunks_device(ctx, wv.as<uint8_t>(), positions ? ctx->tmp_d.as<int32_t>() : nullptr,
+                                   neighbors ? wn.as<int32_t>() : nullptr, wf.as<uint8_t>(), n_chunks, out);
+    if (rc != VX_OK) {
+        wv.release(); wn.release(); wf.release();
+        return rc;
+    }
+    VxMeshBatch *b = *out;
+    b->world_voxels = wv;
+    b->world_neighbors = wn;
+    b->world_flags = wf;
+    b->owns_world = true;
+    b->has_neighbors = neighbors != nullptr;
+    b->has_flags = true;
+    if (neighbors) b->host_neighbors.assign(neighbors, neighbors + n * 6);
+    return VX_OK;
+}
+
+int vx_mesh_batch_update(VxContext *ctx, VxMeshBatch *b, const int32_t *chunk_ids, int32_t n_ids, const uint8_t *voxels,
+                         const uint8_t *uniform_flags, int32_t *n_remeshed) {
+    if (!ctx || !b || n_ids < 0 || (n_ids > 0 && (!chunk_ids || !voxels))) return vx_fail(ctx, VX_ERR_INVALID, "vx_mesh_batch_update: bad argument");
+    if (!b->owns_world) return vx_fail(ctx, VX_ERR_INVALID, "vx_mesh_batch_update: the batch was not created by vx_mesh_chunks (no world copy)");
+    if (n_remeshed) *n_remeshed = 0;
+    if (n_ids == 0) return VX_OK;
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    // edited chunks + the neighbours whose border faces they can change (main.rs:225-280 invalidates the same six)
+    std::vector<int32_t> list;
+    std::vector<uint8_t> seen((size_t)b->n_chunks, 0);
+    for (int32_t i = 0; i < n_ids; ++i) {
+        const int32_t c = chunk_ids[i];
+        if (c < 0 || c >= b->n_chunks) return vx_fail(ctx, VX_ERR_INVALID, "vx_mesh_batch_update: chunk id out of range");
+        if (!seen[c]) { seen[c] = 1; list.push_back(c); }
+    }
+    if (b->has_neighbors)
+        for (int32_t i = 0; i < n_ids; ++i)
+            for (int f = 0; f < 6; ++f) {
+                const int32_t nb = b->host_neighbors[(size_t)chunk_ids[i] * 6 + f];
+                if (nb >= 0 && nb < b->n_chunks && !seen[nb]) { seen[nb] = 1; list.push_back(nb); }
+            }
+    // new voxel data / uniform flags of the edited chunks into the world copy
+    for (int32_t i = 0; i < n_ids; ++i) {
+        VX_CUDA(ctx, cudaMemcpyAsync(b->world_voxels.as<uint8_t>() + (size_t)chunk_ids[i] * VX_CHUNK_VOLUME, voxels + (size_t)i * VX_CHUNK_VOLUME,
+                                     VX_CHUNK_VOLUME, cudaMemcpyHostToDevice, ctx->stream));
+        const uint8_t uf = uniform_flags ? uniform_flags[i] : 0;
+        VX_CUDA(ctx, cudaMemsetAsync(b->world_flags.as<uint8_t>() + chunk_ids[i], uf, 1, ctx->stream));
+    }
+    if (n_remeshed) *n_remeshed = (int32_t)list.size();
+    const uint8_t *d_vox = b->world_voxels.as<uint8_t>();
+    const int32_t *d_nb = b->has_neighbors ? b->world_neighbors.as<int32_t>() : nullptr;
+    const uint8_t *d_uf = b->world_flags.as<uint8_t>();
+    // room behind the live end of the quad stream?  (typical chunk: a few hundred quads; 4096 each is a generous
+    // bound that the overflow flag backs up.)  If not, or if an append overflows, re-mesh the whole world from
+    // scratch, which also drops the dead space.
+    VxMeshBatchInfo info;
+    int rc = vx_mesh_batch_info(ctx, b, &info);
+    if (rc != VX_OK) return rc;
+    bool full = info.total_quads + (int64_t)list.size() * 4096 > b->cap_quads;
+    if (!full) {
+        VX_CUDA(ctx, b->update_ids.reserve(sizeof(int32_t) * list.size()));
+        VX_CUDA(ctx, cudaMemcpyAsync(b->update_ids.ptr, list.data(), sizeof(int32_t) * list.size(), cudaMemcpyHostToDevice, ctx->stream));
+        rc = run_mesher(ctx, d_vox, d_nb, d_uf, b, false, b->update_ids.as<int32_t>(), b->n_chunks, true, (int32_t)list.size());
+        if (rc != VX_OK) return rc;
+        unsigned long long h[4];
+        VX_CUDA(ctx, cudaMemcpyAsync(h, b->cursor.ptr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h[2]) full = true;
+        else b->total_quads = (int64_t)h[0]; // length of the stream, dead space included
+    }
+    if (full) {
+        if (b->cap_quads < info.total_quads + (int64_t)list.size() * 4096) { // also make room for the next updates
+            const int64_t want = info.total_quads * 2 + (int64_t)list.size() * 4096;
+            VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            VX_CUDA(ctx, b->quads.reserve(3 * (size_t)want + 16));
+            b->cap_quads = want;
+        }
+        rc = run_mesher(ctx, d_vox, d_nb, d_uf, b, true);
+        if (rc != VX_OK) return rc;
+    }
+    b->n_meshes = -1; // recounted on demand
+    return VX_OK;
 }
 
 int vx_mesh_batch_info(VxContext *ctx, const VxMeshBatch *b, VxMeshBatchInfo *info) {
@@ -618,6 +704,14 @@ int vx_mesh_batch_info(VxContext *ctx, const VxMeshBatch *b, VxMeshBatchInfo *in
         if (h[2]) return vx_fail(ctx, VX_ERR_CAPACITY, "remesh overflowed the batch quad stream");
         mb->total_quads = (int64_t)h[0];
         mb->n_meshes = (int32_t)h[1];
+    }
+    if (mb->n_meshes < 0) { // after an in-place update: count has_mesh
+        std::vector<uint8_t> hm((size_t)b->n_chunks);
+        if (b->n_chunks) VX_CUDA(ctx, cudaMemcpyAsync(hm.data(), b->has_mesh.ptr, (size_t)b->n_chunks, cudaMemcpyDeviceToHost, ctx->stream));
+        VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int32_t nm = 0;
+        for (uint8_t v : hm) nm += v ? 1 : 0;
+        mb->n_meshes = nm;
     }
     info->n_chunks = b->n_chunks;
     info->n_meshes = mb->n_meshes;
@@ -693,6 +787,7 @@ void vx_mesh_batch_release(VxContext *ctx, VxMeshBatch *b) {
     if (ctx) cudaSetDevice(ctx->device);
     b->quads.release(); b->quad_base.release(); b->quad_count.release(); b->slice_offsets.release();
     b->face_aabb.release(); b->has_mesh.release(); b->positions.release(); b->cursor.release();
+    b->world_voxels.release(); b->world_neighbors.release(); b->world_flags.release(); b->update_ids.release();
     delete b;
 }
 

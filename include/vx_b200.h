@@ -99,7 +99,7 @@ typedef struct {
 typedef struct {
     int32_t n_chunks;
     int32_t n_meshes;     /* chunks with has_mesh != 0 */
-    int64_t total_quads;
+    int64_t total_quads;  /* length of the quad stream (after vx_mesh_batch_update it includes replaced, dead quads) */
 } VxMeshBatchInfo;
 
 /* Raw device pointers of a batch (for zero-copy interop, e.g. NCCL all-gather of quad
@@ -156,6 +156,15 @@ VX_API void vx_host_free(VxContext *ctx, void *p);
  * Host -> device copy, mesh kernel; the result stays on the device. */
 VX_API int vx_mesh_chunks(VxContext *ctx, const uint8_t *voxels, const int32_t *positions, const int32_t *neighbors,
                    const uint8_t *uniform_flags, int32_t n_chunks, VxMeshBatch **out);
+/* Incremental re-mesh of a batch created by vx_mesh_chunks (which keeps a device copy of the world with the batch):
+ * the reference re-meshes an edited chunk and invalidates its six neighbours (main.rs:225-280, world.rs:57-100).
+ *   chunk_ids      n_ids edited chunks (indices into the batch)
+ *   voxels         n_ids x 32768 new voxel data, uniform_flags n_ids (as vx_mesh_chunks) or NULL = all Varied
+ * The edited chunks and the neighbours listed for them at creation are re-meshed in place (*n_remeshed of them); new
+ * quads are appended to the quad stream, the replaced ones become dead space that the next full re-mesh (triggered
+ * automatically when the stream runs out of room) drops.  Every other chunk's mesh is untouched. */
+VX_API int vx_mesh_batch_update(VxContext *ctx, VxMeshBatch *batch, const int32_t *chunk_ids, int32_t n_ids, const uint8_t *voxels,
+                         const uint8_t *uniform_flags, int32_t *n_remeshed);
 /* Same with all four arrays already resident on the context's device. */
 VX_API int vx_mesh_chunks_device(VxContext *ctx, const uint8_t *d_voxels, const int32_t *d_positions,
                           const int32_t *d_neighbors, const uint8_t *d_uniform_flags, int32_t n_chunks,

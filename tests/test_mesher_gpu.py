@@ -217,3 +217,64 @@ def test_chunk_subset_meshing_matches_the_full_batch(ctx, ob):
         merged = sharding.merge_mesh_shards(shards, n, world_size)
         assert np.array_equal(merged["quads"].reshape(-1), ref.quads.reshape(-1)[:merged["quads"].size])
         assert np.array_equal(merged["quad_base"], ref.quad_base) and np.array_equal(merged["has_mesh"], ref.has_mesh)
+
+
+def test_incremental_update_matches_a_full_remesh(ctx, ob):
+    """vx_mesh_batch_update (edit -> re-mesh the chunk and its six neighbours, main.rs:225-280): after every round of
+    edits each chunk's mesh equals the oracle's mesh of the edited world, including the rounds where the quad stream
+    runs out of room and the batch falls back to a full re-mesh."""
+    import vx_scenes
+    pos, world, p, v, nb = vx_scenes.terrain_scene(3)
+    v = v.copy()
+    n = p.shape[0]
+    batch = api.BinaryGreedyMesher.mesh_batch(v, p, nb, None, ctx)
+    rng = np.random.default_rng(11)
+    fell_back = False
+    for rnd in range(12):
+        k = int(rng.integers(1, 9))
+        ids = rng.choice(n, size=k, replace=False).astype(np.int32)
+        for cid in ids.tolist():
+            vol = v[cid].reshape(32, 32, 32)  # [z][y][x]
+            mode = rnd % 4
+            if mode == 0:    # dig a shaft down to y = 0 at a border column (changes the neighbour's border faces)
+                vol[0:3, :, 29:32] = 0
+            elif mode == 1:  # stone pillar on the +X border
+                vol[10:14, :, 31] = 3
+            elif mode == 2:  # noisy block of mixed types: many small quads
+                vol[4:20, 8:24, 4:20] = rng.integers(0, 4, size=(16, 16, 16), dtype=np.uint8)
+            else:            # clear the whole chunk (mesh disappears)
+                vol[...] = 0
+        before = batch.info().total_quads
+        nre = batch.update(ids, v[ids])
+        assert ids.size <= nre <= 7 * ids.size
+        info = batch.info()
+        if info.total_quads < before:
+            fell_back = True  # the stream was rebuilt from scratch
+        ref = ob.mesh_chunks(v, nb, None, p)
+        got = batch.download()
+        assert np.array_equal(got["quad_count"], ref.quad_count), rnd
+        assert np.array_equal(got["has_mesh"], ref.has_mesh) and info.n_meshes == int(ref.has_mesh.sum())
+        assert np.array_equal(got["slice_offsets"], ref.slice_offsets) and np.array_equal(got["face_aabb"], ref.face_aabb)
+        for i in range(n):
+            assert np.array_equal(batch.chunk_quads(i).reshape(-1), ref.chunk_quads(i).reshape(-1)), (rnd, i)
+    # the updated cache renders like a freshly meshed world
+    cam = vx_scenes.path_camera(1, 320, 180)
+    vp = cam.view_projection()
+    cfg = api.default_frame_config(320, 180)
+    c1, d1, s1 = api.render_frame(batch, vp, cam.position, cfg, view_distance=3, ctx=ctx)
+    fresh = api.BinaryGreedyMesher.mesh_batch(v, p, nb, None, ctx)
+    c2, d2, s2 = api.render_frame(fresh, vp, cam.position, cfg, view_distance=3, ctx=ctx)
+    assert np.array_equal(c1, c2) and np.array_equal(d1.view(np.uint32), d2.view(np.uint32)) and np.array_equal(s1, s2)
+    print("fell back to a full re-mesh at least once:", fell_back)
+    fresh.release()
+    batch.release()
+    # a batch that does not own its world refuses the update
+    import torch
+    dv = torch.from_numpy(v).cuda()
+    import ctypes as C
+    h = C.c_void_p()
+    ctx.check(ctx.lib.vx_mesh_chunks_device(ctx.handle, C.c_void_p(dv.data_ptr()), None, None, None, n, C.byref(h)))
+    b2 = api.MeshBatch(ctx, h)
+    with pytest.raises(api.VxError):
+        b2.update(np.array([0], np.int32), v[:1])
+    b2.release()
