@@ -37,4 +37,23 @@ for _ in range(20):
     with torch.cuda.stream(stream):
         flush.fill_(1)
     api.render_frame_device(batch, vp, cam.position, cfgp, VD, ctx); ks += api.frame_kernel_times(ctx)
-print(os.environ.get("VX_B200_LIB", "default"), f"{W}x{H} vd{VD}", "frame ms mean %.4f median %.4f min %.4f | kernels us" % (ms.mean(), np.median(ms), ms.min()), np.round(ks / 20 * 1000, 1))
+import time
+color_host = ctx.host_array((H, W), np.uint32)
+surv_host = np.empty(p.shape[0], dtype=np.int32)
+for _ in range(5):
+    api.render_frame(batch, vp, cam.position, cfg, mesh_ids=None, view_distance=VD, color_out=color_host, want_depth=False, ctx=ctx, survivors_out=surv_host)
+t0 = time.perf_counter()
+for _ in range(200):
+    api.render_frame(batch, vp, cam.position, cfg, mesh_ids=None, view_distance=VD, color_out=color_host, want_depth=False, ctx=ctx, survivors_out=surv_host)
+e2e_us = (time.perf_counter() - t0) / 200 * 1e6
+t0 = time.perf_counter()
+for _ in range(200):
+    api.render_frame_device(batch, vp, cam.position, cfg, VD, ctx)   # synchronous, nothing copied back
+sync_us = (time.perf_counter() - t0) / 200 * 1e6
+t0 = time.perf_counter()
+for _ in range(200):
+    api.render_frame_device(batch, vp, cam.position, cfga, VD, ctx)  # asynchronous submit only
+ctx.synchronize()
+async_us = (time.perf_counter() - t0) / 200 * 1e6
+print("wall us per frame: e2e (mapped host colour) %.1f | synchronous device frame %.1f | async submit, back to back %.1f" % (e2e_us, sync_us, async_us))
+print(os.environ.get("VX_B200_LIB", "default"), f"{W}x{H} vd{VD}", "e2e us %.1f" % e2e_us, "frame ms mean %.4f median %.4f min %.4f | kernels us" % (ms.mean(), np.median(ms), ms.min()), np.round(ks / 20 * 1000, 1))
