@@ -494,6 +494,27 @@ def run_cuda(args):
     big.release()
     del d_big
 
+    # ---- meshing end to end through the host-array entry point (vx_mesh_chunks: voxels in page-locked host memory,
+    #      upload + mesh + the batch header back), the whole world per call
+    mesh_e2e = None
+    if world_size == 1:
+        try:
+            hv = ctx.host_array(v.shape, np.uint8)
+            hv[...] = v
+            for _ in range(2):
+                api.BinaryGreedyMesher.mesh_batch(hv, p, nb, None, ctx, validate=False).release()
+            t0 = time.perf_counter()
+            reps = 10
+            for _ in range(reps):
+                bb = api.BinaryGreedyMesher.mesh_batch(hv, p, nb, None, ctx, validate=False)
+                bb.info()
+                bb.release()
+            el = (time.perf_counter() - t0) / reps
+            mesh_e2e = {"chunks_per_sec": n_chunks / el, "ms_per_world": el * 1e3, "h2d_bytes": int(v.nbytes + nb.nbytes + p.nbytes),
+                        "note": "api.BinaryGreedyMesher.mesh_batch per call: allocate the batch, upload 818 x 32 KiB voxels, mesh, read the totals"}
+        except Exception as e:
+            mesh_e2e = {"error": repr(e)}
+
     # ---- BASELINE cfg 5 on this one GPU (context for the multi-GPU design point): 3840x2160, view distance 32 ------------
     cfg5 = None
     if world_size == 1:
@@ -569,6 +590,7 @@ def run_cuda(args):
             "large_batch_algorithmic_GBps": big_gbs, "large_batch_hbm_frac": big_gbs / peak,
             "cpu_chunks_meshed_per_sec_1_thread": cpu_cps,
             "cfg5_3840x2160_vd32": cfg5,
+            "mesh_e2e_host_arrays": mesh_e2e,
             "reference_published": "162-168 fps on a 6-core i5-12400 (README.md:29-32)",
         },
     }
