@@ -91,6 +91,7 @@ PROTOTYPES = {
     "vx_set_atlas": (C.c_int, [_P, C.POINTER(VxAtlas)]),
     "vx_render_frame": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig), _P, _P, _P, C.POINTER(_I)]),
     "vx_render_frame_device": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig)]),
+    "vx_render_frame_into": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig), _P, _P]),
     "vx_framebuffer_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I), C.POINTER(_I)]),
     "vx_frame_stats": (C.c_int, [_P, C.POINTER(VxFrameStats)]),
     "vx_frame_kernel_times": (C.c_int, [_P, _P]),

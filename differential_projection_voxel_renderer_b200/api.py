@@ -435,6 +435,16 @@ def render_frame_device(batch: MeshBatch, view_proj, camera_position, cfg: VxFra
     ctx.check(ctx.lib.vx_render_frame_device(ctx.handle, batch.handle, None, -1, _p(vp), _p(cam), int(view_distance), C.byref(cfg)))
 
 
+def render_frame_into(batch: MeshBatch, view_proj, camera_position, cfg: VxFrameConfig, view_distance: int, d_color: int,
+                      d_depth: int = 0, ctx: Optional[Context] = None):
+    """vx_render_frame_into: like render_frame_device, the frame goes to the given device-addressable pointers."""
+    ctx = ctx or batch.ctx
+    vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+    cam = np.ascontiguousarray(camera_position, dtype=np.float32).reshape(3)
+    ctx.check(ctx.lib.vx_render_frame_into(ctx.handle, batch.handle, None, -1, _p(vp), _p(cam), int(view_distance), C.byref(cfg),
+                                           C.c_void_p(d_color or None), C.c_void_p(d_depth or None)))
+
+
 def frame_stats(ctx: Context) -> VxFrameStats:
     st = VxFrameStats()
     ctx.check(ctx.lib.vx_frame_stats(ctx.handle, C.byref(st)))

@@ -237,6 +237,12 @@ VX_API int vx_render_frame(VxContext *ctx, const VxMeshBatch *batch, const int32
 VX_API int vx_render_frame_device(VxContext *ctx, const VxMeshBatch *batch, const int32_t *d_mesh_ids, int32_t n_meshes,
                            const float vp[16], const float cam_pos[3], int32_t view_distance,
                            const VxFrameConfig *cfg);
+/* As vx_render_frame_device, but the frame (rows x width, tightly packed) is written to caller-provided memory the
+ * device can address: device memory of this GPU, peer memory of another GPU (stripe composition without a copy), or
+ * device-mapped page-locked host memory.  NULL = the context's own buffer for that plane. */
+VX_API int vx_render_frame_into(VxContext *ctx, const VxMeshBatch *batch, const int32_t *d_mesh_ids, int32_t n_meshes,
+                         const float vp[16], const float cam_pos[3], int32_t view_distance, const VxFrameConfig *cfg,
+                         uint32_t *d_color_dst, float *d_depth_dst);
 /* Device pointers of the last rendered frame: colour (u32) and depth (f32), rows x width. */
 VX_API int vx_framebuffer_device(VxContext *ctx, uint32_t **d_color, float **d_depth, int32_t *rows, int32_t *width);
 VX_API int vx_frame_stats(VxContext *ctx, VxFrameStats *out);

@@ -353,3 +353,23 @@ def test_full_size_frame_3840x2160_vd32_and_its_eight_stripes(ctx, ob):
         parts.append(c)
     assert np.array_equal(np.concatenate(parts), oc)
     batch.release()
+
+
+def test_render_frame_into_caller_device_memory(ctx, ob, scene5):
+    """vx_render_frame_into: a stripe rendered straight into caller-owned device memory (the stripe-gather buffer of the
+    multi-GPU path) equals the oracle rows."""
+    import torch
+    _, p, batch, ref = scene5
+    w, h = 640, 360
+    cam = vx_scenes.path_camera(2, w, h)
+    vp, ids, oc, od, osurv = oracle_frame(ob, ref, p, cam, w, h, 5)
+    dev = torch.device("cuda", 0)
+    for y0, rows in ((0, h), (90, 135), (352, 8)):
+        cfg = api.default_frame_config(w, h)
+        cfg.stripe_y0, cfg.stripe_rows = y0, rows
+        color = torch.zeros((rows, w), dtype=torch.int32, device=dev)
+        depth = torch.zeros((rows, w), dtype=torch.float32, device=dev)
+        api.render_frame_into(batch, vp, cam.position, cfg, 5, color.data_ptr(), depth.data_ptr(), ctx)
+        ctx.synchronize()
+        assert np.array_equal(color.cpu().numpy().view(np.uint32), oc[y0:y0 + rows])
+        assert np.array_equal(depth.cpu().numpy().view(np.uint32), od[y0:y0 + rows].view(np.uint32))
