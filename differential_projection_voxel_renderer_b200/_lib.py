@@ -44,6 +44,10 @@ class VxFrameConfig(C.Structure):
                 ("profile_kernels", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
+class VxTerrainParams(C.Structure):
+    _fields_ = [("perm", C.c_int32 * 512), ("grad", (C.c_double * 2) * 8), ("scale", C.c_double), ("amplitude", C.c_double)]
+
+
 class VxMeshBatchInfo(C.Structure):
     _fields_ = [("n_chunks", C.c_int32), ("n_meshes", C.c_int32), ("total_quads", C.c_int64)]
 
@@ -73,6 +77,7 @@ PROTOTYPES = {
     "vx_context_launch_count": (C.c_int64, [_P]),
     "vx_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "vx_host_free": (None, [_P, _P]),
+    "vx_generate_terrain": (C.c_int, [_P, _P, _I, C.POINTER(VxTerrainParams), _P, _P]),
     "vx_mesh_chunks": (C.c_int, [_P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
     "vx_mesh_batch_update": (C.c_int, [_P, _P, _P, _I, _P, _P, C.POINTER(_I)]),
     "vx_mesh_chunks_device": (C.c_int, [_P, _P, _P, _P, _P, _I, C.POINTER(_P)]),

@@ -16,7 +16,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import VxAtlas, VxError, VxFrameConfig, VxFrameStats, VxMeshBatchDevice, VxMeshBatchInfo
+from ._lib import VxAtlas, VxError, VxFrameConfig, VxFrameStats, VxMeshBatchDevice, VxMeshBatchInfo, VxTerrainParams
 
 CHUNK_SIZE = 32
 CHUNK_VOLUME = 32768
@@ -227,6 +227,32 @@ def upload_mesh_batch(ctx: Context, quads, quad_base, quad_count, slice_offsets,
     h = C.c_void_p()
     ctx.check(ctx.lib.vx_mesh_batch_upload(ctx.handle, _p(quads), C.c_int64(quads.size // 3), *[_p(a) for a in arrs], n, C.byref(h)))
     return MeshBatch(ctx, h)
+
+
+def terrain_params(seed: int = 12345) -> VxTerrainParams:
+    """Noise tables of the host generator (worldgen.py) + chunk.rs:173-177 constants."""
+    from . import worldgen
+    tp = VxTerrainParams()
+    perm = worldgen._perm_table(seed)
+    for i in range(512):
+        tp.perm[i] = int(perm[i])
+    for i in range(8):
+        tp.grad[i][0] = float(worldgen._GRAD2[i, 0])
+        tp.grad[i][1] = float(worldgen._GRAD2[i, 1])
+    tp.scale = 0.01
+    tp.amplitude = 20.0
+    return tp
+
+
+def generate_terrain(positions, d_voxels: int, ctx: Optional[Context] = None, params: Optional[VxTerrainParams] = None) -> np.ndarray:
+    """Chunk::generate_terrain (chunk.rs:114-207) on the device: fills the device array at d_voxels (n x 32768 u8) and
+    returns the uniform flags (n,) u8."""
+    ctx = ctx or default_context()
+    positions = np.ascontiguousarray(positions, dtype=np.int32).reshape(-1, 3)
+    params = params or terrain_params()
+    flags = np.zeros(positions.shape[0], dtype=np.uint8)
+    ctx.check(ctx.lib.vx_generate_terrain(ctx.handle, _p(positions), positions.shape[0], C.byref(params), C.c_void_p(d_voxels), _p(flags)))
+    return flags
 
 
 class BinaryGreedyMesher:

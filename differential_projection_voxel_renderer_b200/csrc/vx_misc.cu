@@ -260,6 +260,99 @@ __global__ void __launch_bounds__(HZ_THREADS) horizon_cull_kernel(HorizonArgs a)
     if (tid == 0) *a.n_kept = (int32_t)s_run;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Terrain generation (Chunk::generate_terrain, chunk.rs:114-207): heightfield
+// h = trunc(noise(x * scale, z * scale) * amplitude) from improved 2-D gradient noise in f64, Grass at y == h, Dirt
+// for h-3 < y < h, Stone below, Air above; chunks entirely above the terrain are Uniform(Air), chunks more than 10
+// below it Uniform(Stone) (chunk.rs:127-134).  One CTA per chunk.  The arithmetic follows worldgen.py operation by
+// operation (this translation unit is compiled -fmad=false), so the voxels equal the host generator's bit for bit.
+// The reference samples the `noise` crate, which is not available here: its exact heights are parity-unpinned
+// (DESIGN.md 5), the permutation / gradient tables are therefore inputs.
+// ------------------------------------------------------------------------------------------------
+struct TerrainArgs {
+    const int32_t *positions; // [n][3]
+    int32_t n;
+    const int32_t *perm;      // [512]
+    double grad[8][2];
+    double scale, amplitude;
+    uint8_t *voxels;          // [n][32768]
+    uint8_t *flags;           // [n]
+};
+
+__device__ __forceinline__ double terrain_fade(double t) { return t * t * t * (t * (t * 6.0 - 15.0) + 10.0); }
+
+__global__ void __launch_bounds__(256) generate_terrain_kernel(TerrainArgs a) {
+    __shared__ int32_t h[32][32]; // [z][x]
+    __shared__ int32_t s_min, s_max;
+    const int tid = threadIdx.x;
+    for (int chunk = blockIdx.x; chunk < a.n; chunk += gridDim.x) {
+        const int cx = a.positions[3 * chunk], cy = a.positions[3 * chunk + 1], cz = a.positions[3 * chunk + 2];
+        if (tid == 0) {
+            s_min = INT32_MAX;
+            s_max = INT32_MIN;
+        }
+        __syncthreads();
+        int mn = INT32_MAX, mx = INT32_MIN;
+        for (int c = tid; c < 1024; c += 256) {
+            const int lz = c >> 5, lx = c & 31;
+            const double x = (double)(cx * VX_CHUNK_SIZE + lx) * a.scale;
+            const double y = (double)(cz * VX_CHUNK_SIZE + lz) * a.scale;
+            const double fx = floor(x), fy = floor(y);
+            const long long xi0 = (long long)fx, yi0 = (long long)fy;
+            const double xf = x - (double)xi0, yf = y - (double)yi0;
+            const int xi = (int)(xi0 & 255), yi = (int)(yi0 & 255);
+            const int aa = a.perm[a.perm[xi] + yi], ab = a.perm[a.perm[xi] + yi + 1];
+            const int ba = a.perm[a.perm[xi + 1] + yi], bb = a.perm[a.perm[xi + 1] + yi + 1];
+            const double u = terrain_fade(xf), v = terrain_fade(yf);
+#define VX_GRAD(hh, dx, dy) (a.grad[(hh) & 7][0] * (dx) + a.grad[(hh) & 7][1] * (dy))
+            const double x1 = VX_GRAD(aa, xf, yf) * (1.0 - u) + VX_GRAD(ba, xf - 1.0, yf) * u;
+            const double x2 = VX_GRAD(ab, xf, yf - 1.0) * (1.0 - u) + VX_GRAD(bb, xf - 1.0, yf - 1.0) * u;
+#undef VX_GRAD
+            double nval = (x1 * (1.0 - v) + x2 * v) * 1.4142135623730951;
+            nval = nval < -1.0 ? -1.0 : (nval > 1.0 ? 1.0 : nval);
+            const int hv = (int)trunc(nval * a.amplitude);
+            h[lz][lx] = hv;
+            mn = min(mn, hv);
+            mx = max(mx, hv);
+        }
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if ((tid & 31) == 0) {
+            atomicMin(&s_min, mn);
+            atomicMax(&s_max, mx);
+        }
+        __syncthreads();
+        const int y0 = cy * VX_CHUNK_SIZE;
+        uint8_t flag = 0;
+        if (y0 > s_max) flag = 1;                          // Uniform(Air)   chunk.rs:127-129
+        else if (y0 + VX_CHUNK_SIZE < s_min - 10) flag = 4; // Uniform(Stone) chunk.rs:132-134
+        if (tid == 0) a.flags[chunk] = flag;
+        uint4 *dst = reinterpret_cast<uint4 *>(a.voxels + (size_t)chunk * VX_CHUNK_VOLUME);
+        for (int r = tid; r < 1024; r += 256) { // r = z*32 + y: one 32-voxel x-row
+            const int lz = r >> 5, wy = y0 + (r & 31);
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int hh = h[lz][4 * j + k];
+                    uint32_t t = 3u;            // Stone
+                    if (wy > hh - 3) t = 2u;    // Dirt
+                    if (wy == hh) t = 1u;       // Grass
+                    if (wy > hh) t = 0u;        // Air
+                    word |= t << (8 * k);
+                }
+                w[j] = flag ? 0u : word;
+            }
+            dst[2 * r] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[2 * r + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+        __syncthreads();
+    }
+}
+
 // vx_div_fast vs the `/` operator on pseudo-random operand pairs.  counters: [0] mismatching quotients among pairs the
 // guard accepted, [1] pairs the guard sent to the fallback, [2] pairs tested.
 __global__ void selftest_division_kernel(unsigned long long seed, unsigned long long n, int mode, unsigned long long *counters) {
@@ -346,6 +439,38 @@ int vx_horizon_cull(VxContext *ctx, const float cam_pos[3], const float *centers
     VX_CHECK_LAUNCH(ctx);
     VX_CUDA(ctx, cudaMemcpyAsync(n_kept, a.n_kept, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     VX_CUDA(ctx, cudaMemcpyAsync(order_inout, a.order, 4 * nn, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+int vx_generate_terrain(VxContext *ctx, const int32_t *positions, int32_t n, const VxTerrainParams *params, uint8_t *d_voxels_out,
+                        uint8_t *uniform_flags_out) {
+    if (!ctx || n < 0 || !params || (n > 0 && (!positions || !d_voxels_out || !uniform_flags_out)))
+        return vx_fail(ctx, VX_ERR_INVALID, "vx_generate_terrain: bad argument");
+    if (n == 0) return VX_OK;
+    if ((reinterpret_cast<uintptr_t>(d_voxels_out) & 15) != 0) return vx_fail(ctx, VX_ERR_INVALID, "voxels must be 16-byte aligned");
+    for (int i = 0; i < 512; ++i)
+        if (params->perm[i] < 0 || params->perm[i] > 255) return vx_fail(ctx, VX_ERR_INVALID, "vx_generate_terrain: permutation entries must be 0..255");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nn = (size_t)n;
+    const size_t off_perm = sizeof(int32_t) * 3 * nn, off_flags = off_perm + sizeof(int32_t) * 512;
+    VX_CUDA(ctx, ctx->tmp_a.reserve(off_flags + nn + 16));
+    uint8_t *base = ctx->tmp_a.as<uint8_t>();
+    VX_CUDA(ctx, cudaMemcpyAsync(base, positions, off_perm, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(base + off_perm, params->perm, sizeof(int32_t) * 512, cudaMemcpyHostToDevice, ctx->stream));
+    TerrainArgs a;
+    a.positions = reinterpret_cast<const int32_t *>(base);
+    a.n = n;
+    a.perm = reinterpret_cast<const int32_t *>(base + off_perm);
+    memcpy(a.grad, params->grad, sizeof(a.grad));
+    a.scale = params->scale;
+    a.amplitude = params->amplitude;
+    a.voxels = d_voxels_out;
+    a.flags = base + off_flags;
+    const int grid = n < ctx->num_sms * 8 ? n : ctx->num_sms * 8;
+    generate_terrain_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+    VX_CHECK_LAUNCH(ctx);
+    VX_CUDA(ctx, cudaMemcpyAsync(uniform_flags_out, a.flags, nn, cudaMemcpyDeviceToHost, ctx->stream));
     VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VX_OK;
 }

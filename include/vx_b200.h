@@ -143,6 +143,24 @@ VX_API int64_t vx_context_launch_count(const VxContext *ctx);
 VX_API int vx_host_alloc(VxContext *ctx, size_t bytes, void **out);
 VX_API void vx_host_free(VxContext *ctx, void *p);
 
+/* ---- terrain generation (the step before meshing) -------------------- */
+
+/* Improved 2-D gradient noise tables + the constants of chunk.rs:173-177 (scale 0.01, amplitude 20). */
+typedef struct {
+    int32_t perm[512];   /* permutation table, doubled (perm[i + 256] == perm[i]), entries 0..255 */
+    double grad[8][2];   /* gradient directions */
+    double scale, amplitude;
+} VxTerrainParams;
+
+/* Chunk::generate_terrain (chunk.rs:114-207) for n chunk positions, on the device: d_voxels_out (device, n x 32768,
+ * 16-byte aligned) receives the voxels of the Varied chunks (zeros for Uniform ones), uniform_flags_out (host, n)
+ * 0 = Varied, 1 = Uniform(Air), 4 = Uniform(Stone) -- the encoding vx_mesh_chunks takes.  Feeding the result to
+ * vx_mesh_chunks_device removes the 32 KiB/chunk upload of a whole-world re-mesh.  The arithmetic reproduces this
+ * repo's host generator (worldgen.py) bit for bit; the reference's own noise crate is not available offline, so its
+ * exact heights are not claimed. */
+VX_API int vx_generate_terrain(VxContext *ctx, const int32_t *positions, int32_t n, const VxTerrainParams *params, uint8_t *d_voxels_out,
+                        uint8_t *uniform_flags_out);
+
 /* ---- meshing ---------------------------------------------------------- */
 
 /* BinaryGreedyMesher::mesh_world (binary_greedy.rs:62-78) / mesh_chunk_in_world (:83) /

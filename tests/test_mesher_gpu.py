@@ -278,3 +278,40 @@ def test_incremental_update_matches_a_full_remesh(ctx, ob):
     with pytest.raises(api.VxError):
         b2.update(np.array([0], np.int32), v[:1])
     b2.release()
+
+
+def test_device_terrain_generation_matches_the_host_generator(ctx, ob):
+    """vx_generate_terrain: voxels and Uniform flags equal worldgen.generate_world bit for bit, and the
+    device-generated world meshes to the same quads without ever being uploaded."""
+    import ctypes as C
+    import torch
+    pos = worldgen.lattice_sphere((1, 0, -2), 6)
+    world = worldgen.generate_world(pos)
+    dev = torch.device("cuda", 0)
+    d_vox = torch.empty((pos.shape[0], 32768), dtype=torch.uint8, device=dev)
+    flags = api.generate_terrain(pos, d_vox.data_ptr(), ctx)
+    assert np.array_equal(flags, world.uniform_flags)
+    assert (flags == 0).sum() > 50 and (flags == 1).sum() > 50 and (flags == 4).sum() > 50
+    got = d_vox.cpu().numpy()
+    assert np.array_equal(got, world.voxels)
+    # far from the origin (large coordinates, negative cells) and another seed
+    far = np.array([[4000, 0, -3999], [-1234, -1, 777], [-1, 0, -1], [255, 0, 256]], dtype=np.int32)
+    w2 = worldgen.generate_world(far, seed=777)
+    d2 = torch.empty((far.shape[0], 32768), dtype=torch.uint8, device=dev)
+    f2 = api.generate_terrain(far, d2.data_ptr(), ctx, api.terrain_params(777))
+    assert np.array_equal(f2, w2.uniform_flags) and np.array_equal(d2.cpu().numpy(), w2.voxels)
+    # mesh straight from the device-resident world
+    nb = world.neighbor_table()
+    d_nb = torch.from_numpy(nb).to(dev)
+    d_fl = torch.from_numpy(flags).to(dev)
+    d_pos = torch.from_numpy(pos).to(dev)
+    h = C.c_void_p()
+    ctx.check(ctx.lib.vx_mesh_chunks_device(ctx.handle, C.c_void_p(d_vox.data_ptr()), C.c_void_p(d_pos.data_ptr()), C.c_void_p(d_nb.data_ptr()),
+                                            C.c_void_p(d_fl.data_ptr()), pos.shape[0], C.byref(h)))
+    batch = api.MeshBatch(ctx, h)
+    ref = ob.mesh_chunks(world.voxels, nb, world.uniform_flags, pos)
+    g = batch.download()
+    assert np.array_equal(g["quad_count"], ref.quad_count) and np.array_equal(g["has_mesh"], ref.has_mesh)
+    for i in np.flatnonzero(ref.has_mesh).tolist():
+        assert np.array_equal(batch.chunk_quads(i).reshape(-1), ref.chunk_quads(i).reshape(-1))
+    batch.release()
