@@ -25,6 +25,9 @@
 
 namespace {
 
+#ifndef VX_MESH_MIN_BLOCKS
+#define VX_MESH_MIN_BLOCKS 5
+#endif
 constexpr int MESH_THREADS = 256;
 constexpr int MESH_WARPS = MESH_THREADS / 32;
 constexpr int PS = 33; // padded row stride of the 32x32 word planes (bank-conflict free both ways)
@@ -290,7 +293,7 @@ __device__ __forceinline__ void process_units(MeshSmem &sm, const ChunkArgs &a, 
     }
 }
 
-__global__ void __launch_bounds__(MESH_THREADS, 5) mesh_chunks_kernel(ChunkArgs a) {
+__global__ void __launch_bounds__(MESH_THREADS, VX_MESH_MIN_BLOCKS) mesh_chunks_kernel(ChunkArgs a) {
     __shared__ MeshSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 

@@ -264,8 +264,8 @@ VX_API int vx_render_frame_into(VxContext *ctx, const VxMeshBatch *batch, const 
 /* Device pointers of the last rendered frame: colour (u32) and depth (f32), rows x width. */
 VX_API int vx_framebuffer_device(VxContext *ctx, uint32_t **d_color, float **d_depth, int32_t *rows, int32_t *width);
 VX_API int vx_frame_stats(VxContext *ctx, VxFrameStats *out);
-/* CUDA-event durations (ms) of the last frame rendered with profile_kernels = 1:
- * [0] cull + draw order, [1] project/clip/setup, [2] stripe-bin fill, [3] span raster + write-out. */
+/* CUDA-event durations (ms) of the last frame rendered with profile_kernels != 0:
+ * [0] cull, [1] rank + project/clip/setup + binning, [2] unused (0), [3] work-item plan + span raster + write-out. */
 VX_API int vx_frame_kernel_times(VxContext *ctx, float ms_out[4]);
 /* Diagnostics: timeline of the raster work items of the last frame rendered with profile_kernels = 2.
  * out: 14 x u64 per item = tile, part | parts << 16, start ns, end ns (%globaltimer), SM id, source entries,
