@@ -48,6 +48,7 @@ struct MeshSmem {
     uint32_t cnt[192];                 // quads per (face, slice)
     uint32_t offs[192];                // exclusive offsets inside the chunk
     uint32_t pstart[192];              // start of the unit's quads in the pool (fast path)
+    uint16_t omap[POOL_CAP];           // final position inside the chunk -> pool position (fast path)
     uint32_t faceTot[6], faceBase[6];
     uint32_t faceRows[6], faceCols[6], faceSlices[6];
     uint32_t occ[3]; // bit s: slice s along x / y / z holds a solid voxel
@@ -241,8 +242,21 @@ __device__ __forceinline__ void unit_rows(const MeshSmem &sm, int face, int slic
 template <int MODE>
 __device__ __forceinline__ void process_units(MeshSmem &sm, const ChunkArgs &a, int tid) {
     const int lane = tid & 31, warp = tid >> 5;
+    // FaceList AABB inputs, accumulated per warp and flushed when the warp moves on to the next face (its units
+    // unit = warp + 8k visit the faces in order, four slices each)
+    uint32_t accRows = 0, accCols = 0, accSlices = 0;
+    int accFace = 0;
     for (int unit = warp; unit < 192; unit += MESH_WARPS) {
         const int face = unit >> 5, slice = unit & 31;
+        if (MODE == 2 && face != accFace) {
+            if (lane == 0 && accSlices) {
+                atomicOr(&sm.faceRows[accFace], accRows);
+                atomicOr(&sm.faceCols[accFace], accCols);
+                atomicOr(&sm.faceSlices[accFace], accSlices);
+            }
+            accRows = accCols = accSlices = 0;
+            accFace = face;
+        }
         if (MODE == 2) {
             // a slice without a solid voxel has no faces: skip it without touching the planes
             if (!((sm.occ[face >> 1] >> slice) & 1u)) {
@@ -267,15 +281,15 @@ __device__ __forceinline__ void process_units(MeshSmem &sm, const ChunkArgs &a, 
             if (lane == 0) {
                 sm.cnt[unit] = n;
                 if (n) {
-                    atomicOr(&sm.faceRows[face], rowsAny);
-                    atomicOr(&sm.faceCols[face], colsAny);
-                    atomicOr(&sm.faceSlices[face], 1u << slice);
                     start = atomicAdd(&sm.pool_used, n);
                     sm.pstart[unit] = start;
                     if (n > (uint32_t)STAGE_CAP || start + n > (uint32_t)POOL_CAP) sm.slow = 1u;
                 }
             }
             if (n) {
+                accRows |= rowsAny;
+                accCols |= colsAny;
+                accSlices |= 1u << slice;
                 start = __shfl_sync(FULL, start, 0);
                 __syncwarp();
                 if (n <= (uint32_t)STAGE_CAP && start + n <= (uint32_t)POOL_CAP)
@@ -290,6 +304,11 @@ __device__ __forceinline__ void process_units(MeshSmem &sm, const ChunkArgs &a, 
                 if (__any_sync(FULL, d[t] != 0)) pos += greedy_warp<1>(d[t], lane, (uint32_t)(t + 1), a.quads, pos, nullptr, nullptr);
             }
         }
+    }
+    if (MODE == 2 && lane == 0 && accSlices) {
+        atomicOr(&sm.faceRows[accFace], accRows);
+        atomicOr(&sm.faceCols[accFace], accCols);
+        atomicOr(&sm.faceSlices[accFace], accSlices);
     }
 }
 
@@ -427,13 +446,18 @@ __global__ void __launch_bounds__(MESH_THREADS, VX_MESH_MIN_BLOCKS) mesh_chunks_
         __syncthreads();
         // ---- output in reference order (face, slice, block type, row, column)
         if (sm.total && !sm.overflow) {
-            if (!sm.slow) { // pool -> quad stream, one warp per unit, 3 bytes per quad
-                for (int unit = warp; unit < 192; unit += MESH_WARPS) {
-                    const uint32_t n = sm.cnt[unit];
-                    if (!n) continue;
-                    const uint32_t *srcq = sm.u.pool + sm.pstart[unit];
-                    uint8_t *dst = a.quads + 3 * (size_t)(sm.base + sm.offs[unit]);
-                    for (uint32_t i = lane; i < 3 * n; i += 32) dst[i] = (uint8_t)(srcq[i / 3] >> (8 * (i % 3)));
+            if (!sm.slow) { // pool -> quad stream: one thread per unit lays out the order map, then one thread per quad
+                if (tid < 192) {
+                    const uint32_t n = sm.cnt[tid], o = sm.offs[tid], ps = sm.pstart[tid];
+                    for (uint32_t k = 0; k < n; ++k) sm.omap[o + k] = (uint16_t)(ps + k);
+                }
+                __syncthreads();
+                uint8_t *dst = a.quads + 3 * (size_t)sm.base;
+                for (uint32_t t = tid; t < sm.total; t += MESH_THREADS) {
+                    const uint32_t q = sm.u.pool[sm.omap[t]];
+                    dst[3 * t] = (uint8_t)q;
+                    dst[3 * t + 1] = (uint8_t)(q >> 8);
+                    dst[3 * t + 2] = (uint8_t)(q >> 16);
                 }
             } else {
                 process_units<1>(sm, a, tid); // rare: more quads than the pool holds
