@@ -16,7 +16,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 pos, world, p, v, nb = vx_scenes.terrain_scene(3)
 ctx = api.Context(0)
 b0 = api.BinaryGreedyMesher.mesh_batch(v, p, nb, None, ctx)
-best = int(np.argmax(b0.download()["quad_count"]))
+qc = b0.download()["quad_count"]
+best = int(np.argsort(qc)[len(qc) // 2]) if len(sys.argv) > 2 and sys.argv[2] == "median" else int(np.argmax(qc))
 dev = torch.device("cuda", 0)
 d_big = torch.from_numpy(v[best]).to(dev).repeat(n, 1).contiguous()
 h = C.c_void_p()
