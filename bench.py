@@ -703,4 +703,9 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    rc = main()
+    # Leave without interpreter-exit destructors: torch frees cached device / page-locked tensors after the CUDA context
+    # is already gone there and aborts the process (exit code 134) although the run has completed.
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(int(rc or 0))
