@@ -664,11 +664,14 @@ def run_cuda(args):
         },
     }
     emit_json_line(out)
-    batch.release()
     if dist is not None:
         return finish_distributed(dist)
-    ctx.close()
-    return 0
+    # The context (and with it the stream torch's allocators have recorded events on) is deliberately NOT torn down
+    # here: freeing the torch tensors after the stream is gone aborts the process.  Leave at once; the driver owns
+    # the process lifetime.
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 _REAL_STDOUT_FD = None

@@ -61,7 +61,7 @@ ctx.check(ctx.lib.vx_frame_setup_trace(ctx.handle, so.ctypes.data_as(C.c_void_p)
 so = so[:ns.value].astype(np.int64)
 so = so[so[:, 0] > 0]
 b0 = so[:, 0].min()
-rel = lambda c: (so[:, c] - b0) / 1000.0
+rel = lambda c: (so[so[:, c] > 0, c] - b0) / 1000.0
 print(f"setup: {so.shape[0]} working CTAs, units/CTA max {so[:, 7].max()}; start mean {rel(0).mean():.1f} max {rel(0).max():.1f} | ranked mean {rel(1).mean():.1f} max {rel(1).max():.1f} | "
       f"projected mean {rel(2).mean():.1f} max {rel(2).max():.1f} | counted mean {rel(8).mean():.1f} max {rel(8).max():.1f} | reserved mean {rel(9).mean():.1f} max {rel(9).max():.1f} | binned mean {rel(3).mean():.1f} max {rel(3).max():.1f} | done mean {rel(4).mean():.1f} max {rel(4).max():.1f}")
 last = so[so[:, 5] > 0]
