@@ -7,18 +7,19 @@
 // Design (one CTA per chunk, persistent over the batch):
 //   stage 1  every thread streams 32-voxel x-rows with two 128-bit loads and SWAR-packs the two
 //            block-type bits of each voxel into two 32-bit words (bits along x) -> 2 x 32 x 32
-//            word bit-planes in shared memory (8 KB instead of the 32 KB byte volume).  Neighbour
-//            chunks contribute six 32x32-bit solid halo planes.
-//   stage 2  face exposure is pure word logic on the planes (A_t & ~S_neighbour; +-X by a 1-bit
-//            shift with the halo bit inserted).  A warp owns one (face, slice) unit: it brings the
-//            exposure mask into the reference orientation (lane = row, bit = column) with a 5-step
-//            shuffle bit-matrix transpose, then runs the greedy merge with the row words in
-//            registers: the run is found with ffs, the row extension with ONE __ballot_sync over
-//            all rows below + ffs, the consumed bits are cleared lane-parallel.
-//   output   quads are emitted in exact reference order (face, slice, block type, row, column).
-//            Pass 1 counts per (face, slice), a CTA scan gives the slice offsets, one atomicAdd
-//            reserves the chunk's range in the batch quad stream, pass 2 re-runs the (cheap) merge
-//            and writes the 3-byte TinyQuads at their final position.
+//            word bit-planes P[y][z] in shared memory (8 KB instead of the 32 KB byte volume).
+//            Neighbour chunks contribute six 32x32-bit solid halo planes, transposed on load.
+//   stage 2  128 warp-level 32x32 bit transposes (5 shuffle steps) give the two other orientations
+//            once per chunk: T[x][y] (bits z) and R[z][x] (bits y), plus slice-occupancy masks.
+//   stage 3  a warp owns one (face, slice) unit; its rows in the reference orientation (lane = row,
+//            bit = column) are plain loads from T / R, exposure is word logic (A_t & ~S_neighbour).
+//            The greedy merge runs with the row words in registers, one iteration per quad: lowest
+//            non-empty row by ballot, run mask by carry propagation, row extension with ONE
+//            __ballot_sync over all rows below, consumed bits cleared lane-parallel.
+//   output   quads are staged per warp and pooled in shared memory; a CTA scan over the 192 unit
+//            counts + one atomicAdd on the batch cursor fix the positions and the pool is copied out
+//            in exact reference order (face, slice, block type, row, column) as 3-byte TinyQuads.
+//            Chunks with more quads than the pool holds re-run the merge and write directly.
 #include "vx_common.cuh"
 
 #include <vector>
