@@ -373,3 +373,18 @@ def test_render_frame_into_caller_device_memory(ctx, ob, scene5):
         ctx.synchronize()
         assert np.array_equal(color.cpu().numpy().view(np.uint32), oc[y0:y0 + rows])
         assert np.array_equal(depth.cpu().numpy().view(np.uint32), od[y0:y0 + rows].view(np.uint32))
+
+
+@pytest.mark.parametrize("wh", [(1, 1), (3, 5), (129, 9), (130, 17), (257, 33), (1000, 7), (7, 1000), (2048, 16)])
+def test_odd_framebuffer_sizes(ctx, ob, scene5, wh):
+    """Widths that are not multiples of 4 (scalar write-out path), partial tiles in both directions, single-pixel
+    and very wide / very tall targets: the whole frame stays bit-identical."""
+    _, p, batch, ref = scene5
+    w, h = wh
+    cam = camera.Camera((0.0, 10.0, 20.0), w / h, yaw=0.2, pitch=-0.1)
+    vp, ids, oc, od, osurv = oracle_frame(ob, ref, p, cam, w, h, 5, threads=2)
+    cfg = api.default_frame_config(w, h)
+    color, depth, surv = api.render_frame(batch, vp, cam.position, cfg, mesh_ids=ids, ctx=ctx)
+    assert np.array_equal(surv, osurv)
+    assert np.array_equal(depth.view(np.uint32), od.view(np.uint32))
+    assert np.array_equal(color, oc)
