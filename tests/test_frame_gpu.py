@@ -388,3 +388,38 @@ def test_odd_framebuffer_sizes(ctx, ob, scene5, wh):
     assert np.array_equal(surv, osurv)
     assert np.array_equal(depth.view(np.uint32), od.view(np.uint32))
     assert np.array_equal(color, oc)
+
+
+def test_random_cameras_bit_exact(ctx, ob, scene5):
+    """Twenty seeded random cameras (inside and outside the terrain, steep pitches, narrow and wide fields of view, a
+    near plane far out) plus arbitrary non-camera matrices (rolled / sheared views): bit-identical frames."""
+    _, p, batch, ref = scene5
+    w, h = 320, 180
+    rng = np.random.default_rng(2026)
+    cfg = api.default_frame_config(w, h)
+    mats = []
+    for i in range(20):
+        cam = camera.Camera(rng.uniform([-150, -30, -150], [150, 80, 150]), w / h, yaw=float(rng.uniform(-np.pi, np.pi)),
+                            pitch=float(rng.uniform(-1.5, 1.5)), fov_deg=float(rng.choice([20.0, 45.0, 70.0, 110.0, 150.0])),
+                            near=float(rng.choice([0.1, 0.01, 5.0])))
+        mats.append((cam.view_projection(), cam.position))
+    for i in range(6):  # rolled camera: rotate the view about its forward axis, plus a random shear
+        cam = camera.Camera(rng.uniform([-80, 5, -80], [80, 40, 80]), w / h, yaw=float(rng.uniform(-3, 3)), pitch=float(rng.uniform(-0.6, 0.6)))
+        vp = cam.view_projection().reshape(4, 4).T.astype(np.float64)  # row-major P*V
+        a = float(rng.uniform(-np.pi, np.pi))
+        roll = np.array([[np.cos(a), -np.sin(a), 0, 0], [np.sin(a), np.cos(a), 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+        shear = np.eye(4)
+        shear[0, 1] = rng.uniform(-0.3, 0.3)
+        m = (shear @ roll @ vp).astype(np.float32)
+        mats.append((np.ascontiguousarray(m.T.reshape(16)), cam.position))
+    covered = 0
+    for vp, campos in mats:
+        vis = ob.cull_chunks(p, vp, campos, 5)
+        ids = np.flatnonzero((vis != 0) & (ref.has_mesh != 0)).astype(np.int32)
+        oc, od, osurv = ob.render_frame(ref, ids, vp, campos, ob.default_frame_config(w, h, n_threads=3), ob.default_atlas())
+        color, depth, surv = api.render_frame(batch, vp, campos, cfg, mesh_ids=ids, ctx=ctx)
+        assert np.array_equal(surv, osurv)
+        assert np.array_equal(depth.view(np.uint32), od.view(np.uint32))
+        assert np.array_equal(color, oc)
+        covered += int((color != cfg.clear_color).sum())
+    assert covered > 100000
