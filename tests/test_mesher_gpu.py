@@ -106,6 +106,27 @@ def test_random_chunks_and_regrow(ctx, ob):
     assert ref.quad_count[4] > 49152
 
 
+def test_shared_memory_pool_boundaries(ctx, ob):
+    """The mesher keeps a chunk's quads in a 2112-entry shared-memory pool (128 per (face, slice) unit while staging)
+    and falls back to a second emitting pass beyond that: exactly full, one past full, one unit of 128 / 129 / 512
+    quads."""
+    def isolated(cells):
+        c = kat.empty_chunk().reshape(32, 32, 32)  # [z][y][x]
+        for (x, y, z) in cells:
+            c[z, y, x] = 1 + (x + y + z) % 3
+        return c.reshape(-1)
+    grid = [(2 * i, 2 * j, 2 * k) for i in range(8) for j in range(11) for k in range(4)]
+    assert len(grid) == 352
+    exactly_full = isolated(grid)                    # 352 voxels x 6 faces = 2112 quads, <= 88 per unit
+    one_more = isolated(grid + [(16, 0, 8)])          # 2118 quads: second pass
+    row128 = isolated([(2 * i, 0, 2 * k) for i in range(16) for k in range(8)])    # +-Y units of slice 0: 128 quads each
+    row129 = isolated([(2 * i, 0, 2 * k) for i in range(16) for k in range(8)] + [(1, 0, 17)])
+    plane512 = isolated([(x, 0, z) for x in range(32) for z in range(32) if (x + z) % 2 == 0])  # 512 per +-Y unit
+    vox = np.stack([exactly_full, one_more, row128, row129, plane512])
+    ref = run_both(ctx, ob, vox, None)
+    assert ref.quad_count.tolist()[:2] == [2112, 2118]
+
+
 def test_full_size_properties(ctx, ob):
     """BASELINE size (cfg 3: every Varied chunk of the vd-12 world): size-independent checks on the whole batch
     + bit-exact comparison of a sample of chunks (the oracle meshes ~1.3k chunks/s)."""
