@@ -272,9 +272,8 @@ VX_API int vx_frame_kernel_times(VxContext *ctx, float ms_out[4]);
  * keys-ready ns, first-expansion ns, first-task-round ns, then for thread 0's first task the clock cycles spent on
  * record load, edge setup, span setup + jump, pixel walk, and its pixel count. */
 VX_API int vx_frame_trace(VxContext *ctx, uint64_t *out, int32_t cap_items, int32_t *n_items);
-/* Same for the setup kernel: 12 x u64 per CTA = start, ranked, projected, binned, done (ns), plan start, plan end (last
- * CTA only), units processed, counted, ranges reserved, plan counters loaded, plan items written.  CTAs that had no
- * unit stay all-zero. */
+/* Same for the setup kernel: 12 x u64 per CTA = start, ranked, projected, binned, done (ns), tiles in the unit's box,
+ * triangles kept, units processed, counted, ranges reserved (ns), 2 unused.  CTAs that had no unit stay all-zero. */
 VX_API int vx_frame_setup_trace(VxContext *ctx, uint64_t *out, int32_t cap_ctas, int32_t *n_ctas);
 /* Diagnostics: triangles binned per 128x8 tile in the last frame (row-major tile grid, ntx x nty). */
 VX_API int vx_frame_bin_counts(VxContext *ctx, uint32_t *counts_out, int32_t cap, int32_t *ntx, int32_t *nty);

@@ -64,7 +64,11 @@ b0 = so[:, 0].min()
 rel = lambda c: (so[so[:, c] > 0, c] - b0) / 1000.0
 print(f"setup: {so.shape[0]} working CTAs, units/CTA max {so[:, 7].max()}; start mean {rel(0).mean():.1f} max {rel(0).max():.1f} | ranked mean {rel(1).mean():.1f} max {rel(1).max():.1f} | "
       f"projected mean {rel(2).mean():.1f} max {rel(2).max():.1f} | counted mean {rel(8).mean():.1f} max {rel(8).max():.1f} | reserved mean {rel(9).mean():.1f} max {rel(9).max():.1f} | binned mean {rel(3).mean():.1f} max {rel(3).max():.1f} | done mean {rel(4).mean():.1f} max {rel(4).max():.1f}")
-last = so[so[:, 5] > 0]
+slow = np.argsort(-(so[:, 4] - so[:, 0]))[:8]
+for i in slow:
+    r = [(so[i, c] - b0) / 1000.0 if so[i, c] > 0 else float("nan") for c in (0, 1, 2, 8, 9, 3, 4)]
+    print("  slow setup CTA: start %.1f ranked %.1f projected %.1f counted %.1f reserved %.1f binned %.1f done %.1f us | box tiles %d, triangles %d" % (*r, so[i, 5], so[i, 6]))
+last = so[so[:, 10] > 0]
 if last.shape[0]:
     print(f"setup plan: start {(last[0, 5] - b0) / 1000:.1f} loaded {(last[0, 10] - b0) / 1000:.1f} written {(last[0, 11] - b0) / 1000:.1f} end {(last[0, 6] - b0) / 1000:.1f} us;  raster first item starts {(base - b0) / 1000:.1f} us after the first setup CTA")
 st = api.frame_stats(ctx)
