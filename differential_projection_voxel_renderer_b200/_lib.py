@@ -48,6 +48,11 @@ class VxTerrainParams(C.Structure):
     _fields_ = [("perm", C.c_int32 * 512), ("grad", (C.c_double * 2) * 8), ("scale", C.c_double), ("amplitude", C.c_double)]
 
 
+class VxFacePacket32(C.Structure):
+    _fields_ = [("len", C.c_uint8), ("u_min", C.c_uint8 * 32), ("v_min", C.c_uint8 * 32), ("u_len", C.c_uint8 * 32),
+                ("v_len", C.c_uint8 * 32), ("axis_pos", C.c_uint8 * 32), ("block_type", C.c_uint8 * 32), ("pad", C.c_uint8 * 31)]
+
+
 class VxMeshBatchInfo(C.Structure):
     _fields_ = [("n_chunks", C.c_int32), ("n_meshes", C.c_int32), ("total_quads", C.c_int64)]
 
@@ -104,6 +109,7 @@ PROTOTYPES = {
     "vx_frame_setup_trace": (C.c_int, [_P, _P, _I, C.POINTER(_I)]),
     "vx_frame_bin_counts": (C.c_int, [_P, _P, _I, C.POINTER(_I), C.POINTER(_I)]),
     "vx_render_mesh": (C.c_int, [_P, _P, _I, _P, C.POINTER(VxFrameConfig), _P, _P, _P]),
+    "vx_face_packets": (C.c_int, [_P, _P, _I, _P, _I, _P]),
     "vx_face_basis": (C.c_int, [_P, _P, _P, _P, _I, _P, _P]),
     "vx_project_packet": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "vx_transform_vertices": (C.c_int, [_P, _P, _I, _P, _P, _P]),

@@ -498,6 +498,27 @@ def framebuffer_device(ctx: Context):
     return dc.value, dd.value, rows.value, width.value
 
 
+def face_packets(batch: MeshBatch, mesh_id: int, ctx: Optional[Context] = None):
+    """ChunkFacePackets::from_chunk_mesh (face_packets.rs:122-174): list of 6 lists of dicts with the SoA arrays of each
+    FacePacket32 (len, u_min, v_min, u_len, v_len, axis_pos, block_type as u8 arrays of 32)."""
+    ctx = ctx or batch.ctx
+    per_face = (C.c_int32 * 6)()
+    h = batch._host or batch.download()
+    cap = max(1, (int(h["quad_count"][mesh_id]) + 31) // 32 + 6)
+    arr = (_lib.VxFacePacket32 * cap)()
+    ctx.check(ctx.lib.vx_face_packets(ctx.handle, batch.handle, int(mesh_id), arr, cap, per_face))
+    out, k = [], 0
+    for f in range(6):
+        lst = []
+        for _ in range(per_face[f]):
+            pk = arr[k]
+            lst.append({"len": int(pk.len), **{name: np.ctypeslib.as_array(getattr(pk, name)).copy()
+                                               for name in ("u_min", "v_min", "u_len", "v_len", "axis_pos", "block_type")}})
+            k += 1
+        out.append(lst)
+    return out
+
+
 class FaceBasis:
     """differential_projection.rs:18-82: origin, tangent, bitangent, normal in clip space."""
 

@@ -353,6 +353,52 @@ __global__ void __launch_bounds__(256) generate_terrain_kernel(TerrainArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// ChunkFacePackets::from_chunk_mesh (face_packets.rs:122-174): the quads of a mesh regrouped per face into SoA
+// packets of up to 32 (FacePacket32 :13-25), in list order (slice by slice), axis_pos = slice + 1 for positive faces.
+// One thread per quad; unused lanes of the last packet of a face stay zero (FacePacket32::new).
+// ------------------------------------------------------------------------------------------------
+__global__ void face_packets_kernel(const uint8_t *quads, const uint32_t *slice_offsets, uint32_t qbase, uint32_t qcount,
+                                    VxFacePacket32 *out, uint32_t cap_packets) {
+    __shared__ uint32_t so[198];
+    __shared__ uint32_t pbase[7]; // first packet of each face
+    for (int i = threadIdx.x; i < 198; i += blockDim.x) so[i] = slice_offsets[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int f = 0; f < 6; ++f) {
+            pbase[f] = run;
+            run += (so[f * 33 + 32] - so[f * 33] + 31u) / 32u;
+        }
+        pbase[6] = run;
+    }
+    __syncthreads();
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < qcount; q += gridDim.x * blockDim.x) {
+        int face = 0;
+        for (int ff = 1; ff < 6; ++ff) face += (so[ff * 33] <= q) ? 1 : 0;
+        int lo = 0, hi = 31;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (so[face * 33 + mid] <= q) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t in_face = q - so[face * 33];
+        const uint32_t pk = pbase[face] + in_face / 32u, lane = in_face % 32u;
+        if (pk >= cap_packets) continue;
+        const uint8_t *qp = quads + 3 * (size_t)(qbase + q);
+        const uint32_t b0 = qp[0], b1 = qp[1], b2 = qp[2];
+        VxFacePacket32 &P = out[pk];
+        P.u_min[lane] = (uint8_t)(b0 & 0x1F);
+        P.v_min[lane] = (uint8_t)(((b0 >> 5) & 7) | ((b1 & 3) << 3)); // TinyQuad accessors mesh.rs:309-341
+        P.u_len[lane] = (uint8_t)(((b1 >> 2) & 0x3F) + 1);
+        P.v_len[lane] = (uint8_t)((b2 & 0x3F) + 1);
+        P.axis_pos[lane] = (uint8_t)((face & 1) ? lo : lo + 1);
+        P.block_type[lane] = (uint8_t)((b2 >> 6) & 3);
+        const uint32_t face_quads = so[face * 33 + 32] - so[face * 33];
+        if (lane == 0) P.len = (uint8_t)min(32u, face_quads - (in_face / 32u) * 32u);
+    }
+}
+
 // vx_div_fast vs the `/` operator on pseudo-random operand pairs.  counters: [0] mismatching quotients among pairs the
 // guard accepted, [1] pairs the guard sent to the fallback, [2] pairs tested.
 __global__ void selftest_division_kernel(unsigned long long seed, unsigned long long n, int mode, unsigned long long *counters) {
@@ -471,6 +517,35 @@ int vx_generate_terrain(VxContext *ctx, const int32_t *positions, int32_t n, con
     generate_terrain_kernel<<<grid, 256, 0, ctx->stream>>>(a);
     VX_CHECK_LAUNCH(ctx);
     VX_CUDA(ctx, cudaMemcpyAsync(uniform_flags_out, a.flags, nn, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+int vx_face_packets(VxContext *ctx, const VxMeshBatch *batch, int32_t mesh_id, VxFacePacket32 *packets_out, int32_t cap_packets,
+                    int32_t n_packets_per_face[6]) {
+    if (!ctx || !batch || !n_packets_per_face || cap_packets < 0 || (cap_packets > 0 && !packets_out))
+        return vx_fail(ctx, VX_ERR_INVALID, "vx_face_packets: bad argument");
+    if (mesh_id < 0 || mesh_id >= batch->n_chunks) return vx_fail(ctx, VX_ERR_INVALID, "mesh id out of range");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint32_t so[198], qb = 0, qc = 0;
+    VX_CUDA(ctx, cudaMemcpyAsync(so, batch->slice_offsets.as<uint32_t>() + (size_t)mesh_id * 198, sizeof(so), cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(&qb, batch->quad_base.as<uint32_t>() + mesh_id, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(&qc, batch->quad_count.as<uint32_t>() + mesh_id, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int32_t total = 0;
+    for (int f = 0; f < 6; ++f) {
+        n_packets_per_face[f] = (int32_t)((so[f * 33 + 32] - so[f * 33] + 31u) / 32u);
+        total += n_packets_per_face[f];
+    }
+    if (total > cap_packets) return vx_fail(ctx, VX_ERR_CAPACITY, "vx_face_packets: packet array too small (sizes are in n_packets_per_face)");
+    if (total == 0) return VX_OK;
+    VX_CUDA(ctx, ctx->tmp_a.reserve(sizeof(VxFacePacket32) * (size_t)total));
+    VX_CUDA(ctx, cudaMemsetAsync(ctx->tmp_a.ptr, 0, sizeof(VxFacePacket32) * (size_t)total, ctx->stream));
+    const int blocks = (int)((qc + 255u) / 256u);
+    face_packets_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, ctx->stream>>>(batch->quads.as<uint8_t>(), batch->slice_offsets.as<uint32_t>() + (size_t)mesh_id * 198,
+                                                                      qb, qc, ctx->tmp_a.as<VxFacePacket32>(), (uint32_t)total);
+    VX_CHECK_LAUNCH(ctx);
+    VX_CUDA(ctx, cudaMemcpyAsync(packets_out, ctx->tmp_a.ptr, sizeof(VxFacePacket32) * (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
     VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VX_OK;
 }

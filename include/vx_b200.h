@@ -286,6 +286,21 @@ VX_API int vx_render_mesh(VxContext *ctx, const VxMeshBatch *batch, int32_t mesh
 
 /* ---- hyper-pipeline pieces ------------------------------------------- */
 
+/* `FacePacket32` face_packets.rs:13-25: up to 32 quads of one face direction, structure of arrays, 32-byte aligned. */
+typedef struct {
+    uint8_t len;
+    uint8_t u_min[32], v_min[32], u_len[32], v_len[32];
+    uint8_t axis_pos[32];   /* slice + 1 for positive faces, slice for negative ones (:146-151) */
+    uint8_t block_type[32];
+    uint8_t pad[31];        /* align(32): sizeof == 224 */
+} VxFacePacket32;
+
+/* ChunkFacePackets::from_chunk_mesh (face_packets.rs:122-174) for one mesh of a batch: packets of face 0 first, then
+ * face 1 ... (FaceDir order), n_packets_per_face[f] of them; packets_out must hold their sum (<= cap_packets, else
+ * VX_ERR_CAPACITY with the sizes filled in).  The arrays of a packet feed vx_project_packet directly. */
+VX_API int vx_face_packets(VxContext *ctx, const VxMeshBatch *batch, int32_t mesh_id, VxFacePacket32 *packets_out, int32_t cap_packets,
+                    int32_t n_packets_per_face[6]);
+
 /* FaceBasis::from_face_direction (differential_projection.rs:37-62) for n (face, chunk, slice) triples.
  * basis_out: n x 16 f32 = origin, tangent, bitangent, normal. */
 VX_API int vx_face_basis(VxContext *ctx, const int32_t *faces, const int32_t *chunk_pos, const uint8_t *slice_idx, int32_t n,

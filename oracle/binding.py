@@ -204,6 +204,32 @@ def render_frame(mb: MeshBatch, mesh_ids, vp, cam_pos, cfg: FrameConfig, atlas: 
     return color, depth, surv[:k].copy()
 
 
+def face_packets(mb: "MeshBatch", mesh_id: int):
+    """ChunkFacePackets::from_chunk_mesh + FacePacketBuilder (face_packets.rs:72-174), restated with plain loops:
+    6 lists of packets, each a dict of len + the six u8[32] arrays (unused lanes zero, FacePacket32::new :28-38)."""
+    so = mb.slice_offsets[mesh_id]
+    quads = unpack_quads(mb.chunk_quads(mesh_id))
+    faces = []
+    for f in range(6):
+        packets, cur = [], None
+        for s in range(32):
+            axis_pos = s + 1 if f % 2 == 0 else s  # :146-151
+            for q in range(int(so[f, s]), int(so[f, s + 1])):
+                if cur is None or cur["len"] >= 32:  # FacePacketBuilder::push :93-99
+                    if cur is not None:
+                        packets.append(cur)
+                    cur = {"len": 0, **{k: np.zeros(32, dtype=np.uint8) for k in ("u_min", "v_min", "u_len", "v_len", "axis_pos", "block_type")}}
+                u, v, w, h, bt = (int(x) for x in quads[q])
+                i = cur["len"]
+                cur["u_min"][i], cur["v_min"][i], cur["u_len"][i], cur["v_len"][i] = u, v, w, h
+                cur["axis_pos"][i], cur["block_type"][i] = axis_pos, bt
+                cur["len"] = i + 1
+        if cur is not None and cur["len"] > 0:  # finish :102-107
+            packets.append(cur)
+        faces.append(packets)
+    return faces
+
+
 def face_basis(face, chunk_pos, slice_idx, vp) -> np.ndarray:
     vp = np.ascontiguousarray(vp, dtype=np.float32).reshape(16)
     cp = np.ascontiguousarray(chunk_pos, dtype=np.int32).reshape(3)

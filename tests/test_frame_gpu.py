@@ -423,3 +423,30 @@ def test_random_cameras_bit_exact(ctx, ob, scene5):
         assert np.array_equal(color, oc)
         covered += int((color != cfg.clear_color).sum())
     assert covered > 100000
+
+
+def test_face_packets_match_the_oracle_and_feed_the_projection(ctx, ob, scene5):
+    """vx_face_packets (ChunkFacePackets::from_chunk_mesh, face_packets.rs:122-174) on terrain meshes; a packet's SoA
+    arrays go straight into the packet projection."""
+    _, p, batch, ref = scene5
+    vp = vx_scenes.path_camera(1, 1280, 720).view_projection()
+    checked = 0
+    for mesh_id in np.flatnonzero(ref.has_mesh)[:8].tolist():
+        got = api.face_packets(batch, mesh_id, ctx)
+        want = ob.face_packets(ref, mesh_id)
+        for f in range(6):
+            assert len(got[f]) == len(want[f])
+            for g, w_ in zip(got[f], want[f]):
+                assert g["len"] == w_["len"]
+                for k in ("u_min", "v_min", "u_len", "v_len", "axis_pos", "block_type"):
+                    assert np.array_equal(g[k], w_[k]), (mesh_id, f, k)
+                checked += 1
+        f = max(range(6), key=lambda ff: len(got[ff]))
+        pk = got[f][0]
+        n = pk["len"]
+        basis = api.FaceBasis.from_face_direction(f, p[mesh_id], int(pk["axis_pos"][0]) - (1 if f % 2 == 0 else 0), vp, ctx)
+        outs = basis.project_packet_bounds(pk["u_min"][:n], pk["v_min"][:n], pk["u_len"][:n], pk["v_len"][:n], ctx)
+        wants = ob.project_packet(basis.matrix, pk["u_min"][:n], pk["v_min"][:n], pk["u_len"][:n], pk["v_len"][:n])
+        for a_, b_ in zip(outs, wants):
+            assert np.array_equal(a_.view(np.uint32), b_.view(np.uint32))
+    assert checked > 20

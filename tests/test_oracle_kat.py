@@ -261,3 +261,23 @@ def test_near_plane_clip(ob):  # src/rendering/rasterizer.rs:166-247: camera ins
     ob.render_mesh(mb, 0, cam.view_projection(), cfg, ob.default_atlas(), (0, 0, 320, 180), color, depth)
     assert int((color != cfg.clear_color).sum()) > 0
     assert not np.isnan(depth).any()
+
+
+def test_face_packets_single_voxel_and_split(ob):  # face_packets.rs:184-228
+    c = kat.empty_chunk().reshape(32, 32, 32)
+    c[16, 16, 16] = kat.STONE
+    m = ob.mesh_chunks(c.reshape(1, -1))
+    pk = ob.face_packets(m, 0)
+    for f in range(6):
+        assert len(pk[f]) == 1 and pk[f][0]["len"] == 1 and pk[f][0]["block_type"][0] == kat.STONE
+        assert pk[f][0]["axis_pos"][0] == (17 if f % 2 == 0 else 16)
+    # 2 * 32 + 5 isolated voxels in one y-slice: the +Y face splits into packets of 32, 32, 5, filled sequentially
+    c = kat.empty_chunk().reshape(32, 32, 32)
+    cells = [(2 * (i % 16), 2 * (i // 16)) for i in range(69)]
+    for x, z in cells:
+        c[z, 3, x] = kat.GRASS
+    m = ob.mesh_chunks(c.reshape(1, -1))
+    pk = ob.face_packets(m, 0)
+    assert [p["len"] for p in pk[2]] == [32, 32, 5]
+    assert all(int(p["axis_pos"][0]) == 4 for p in pk[2]) and all(int(p["axis_pos"][0]) == 3 for p in pk[3])
+    assert pk[2][2]["u_len"][5:].sum() == 0  # unused lanes stay zero
