@@ -450,3 +450,32 @@ def test_face_packets_match_the_oracle_and_feed_the_projection(ctx, ob, scene5):
         for a_, b_ in zip(outs, wants):
             assert np.array_equal(a_.view(np.uint32), b_.view(np.uint32))
     assert checked > 20
+
+
+def test_orthographic_subpixel_quads(ctx, ob):
+    """The pixel-centre KAT scenes of tests/test_oracle_kat.py (orthographic matrices, w == 1, quads a fraction of a
+    pixel wide or tall) through vx_render_mesh: identical to the oracle, pixel for pixel."""
+    from test_oracle_kat import _ortho_vp
+    w, h = 64, 48
+    c = kat.empty_chunk()
+    kat.set_block(c, 4, 4, 4, kat.STONE)
+    vox = c.reshape(1, -1)
+    batch = api.BinaryGreedyMesher.mesh_batch(vox, [(0, 0, 0)], None, None, ctx)
+    ref = ob.mesh_chunks(vox)
+    ocfg, atlas = ob.default_frame_config(w, h), ob.default_atlas()
+    ocfg.backface_culling = 0
+    r = api.Rasterizer(ctx)
+    r.backface_culling = False
+    drawn = 0
+    for lo, hi in ((10.1, 10.9), (10.0, 10.5), (10.6, 11.6), (10.1, 11.9), (10.4, 10.6), (10.0, 11.0), (10.0, 10.4), (10.6, 11.0), (0.2, 63.9), (-5.0, 3.3)):
+        for vp in (_ortho_vp(w, h, lo, hi, 20.25, 29.75), _ortho_vp(w, h, 20.25, 29.75, lo, min(hi, 47.7))):
+            fb = api.Framebuffer(w, h)
+            fb.clear(0xFF87CEEB)
+            oc, od = fb.color_buffer.copy(), fb.depth_buffer.copy()
+            ob.render_mesh(ref, 0, vp, ocfg, atlas, (0, 0, w, h), oc, od)
+            r.render_mesh(batch, 0, vp, fb)
+            assert np.array_equal(fb.color_buffer, oc), (lo, hi)
+            assert np.array_equal(fb.depth_buffer.view(np.uint32), od.view(np.uint32)), (lo, hi)
+            drawn += int((oc != 0xFF87CEEB).sum())
+    assert drawn > 500
+    batch.release()

@@ -281,3 +281,47 @@ def test_face_packets_single_voxel_and_split(ob):  # face_packets.rs:184-228
     assert [p["len"] for p in pk[2]] == [32, 32, 5]
     assert all(int(p["axis_pos"][0]) == 4 for p in pk[2]) and all(int(p["axis_pos"][0]) == 3 for p in pk[3])
     assert pk[2][2]["u_len"][5:].sum() == 0  # unused lanes stay zero
+
+
+def _ortho_vp(w, h, x0, x1, y0, y1, voxel=(4, 4)):
+    """Column-major VP (w == 1 everywhere) that maps the unit +Z face of voxel `voxel` to the screen rectangle
+    [x0, x1] x [y0, y1] (pixels, y down)."""
+    vx, vy = voxel
+    ax = 2.0 * (x1 - x0) / w                  # ndc_x = ax * (X - vx) + (2 x0 / w - 1)
+    ay = 2.0 * (y1 - y0) / h                  # world y up -> screen y down: the top edge (Y = vy + 1) lands on y0
+    m = np.zeros((4, 4), dtype=np.float64)    # row-major here
+    m[0, 0], m[0, 3] = ax, (2.0 * x0 / w - 1.0) - ax * vx
+    m[1, 1], m[1, 3] = ay, (1.0 - 2.0 * y1 / h) - ay * vy
+    m[2, 2], m[2, 3] = 0.001, 0.5
+    m[3, 3] = 1.0
+    return np.ascontiguousarray(m.T.reshape(16).astype(np.float32))
+
+
+@pytest.mark.parametrize("lo,hi,n", [(10.1, 10.9, 1), (10.0, 10.5, 1), (10.6, 11.6, 1), (10.1, 11.9, 2), (10.4, 10.6, 1), (10.0, 11.0, 1),
+                                      (10.0, 10.4, 0), (10.6, 11.0, 0)])
+def test_pixel_centre_coverage_rules(ob, lo, hi, n):
+    """tests/rasterizer_gap_test.rs:6-106 and tests/rasterizer_x_gap_test.rs:3-80: a pixel is drawn iff its centre lies in
+    the span, in x (`ceil(x0 - 0.5) ..= floor(x1 - 0.5)`, rasterizer.rs:1408-1409) and in y (half-open edge test at
+    `y + 0.5`, :1357-1390).  The reference checks the arithmetic; here the restated rasterizer itself is driven with a
+    quad that spans exactly [lo, hi] in one axis and a comfortable [20.25, 29.75] in the other."""
+    w, h = 64, 48
+    c = kat.empty_chunk()
+    kat.set_block(c, 4, 4, 4, kat.STONE)
+    mb = ob.mesh_chunks(c.reshape(1, -1))
+    cfg = ob.default_frame_config(w, h)
+    cfg.backface_culling = 0
+    for axis in ("x", "y"):
+        if axis == "y" and hi == 10.5:
+            continue  # rows use the half-open edge test (:1363-1390): a quad ending exactly ON a centre is left to rounding
+        vp = _ortho_vp(w, h, lo, hi, 20.25, 29.75) if axis == "x" else _ortho_vp(w, h, 20.25, 29.75, lo, hi)
+        color = np.full((h, w), cfg.clear_color, dtype=np.uint32)
+        depth = np.full((h, w), np.inf, dtype=np.float32)
+        ob.render_mesh(mb, 0, vp, cfg, ob.default_atlas(), (0, 0, w, h), color, depth)
+        cov = color != cfg.clear_color
+        cols, rows = np.flatnonzero(cov.any(axis=0)), np.flatnonzero(cov.any(axis=1))
+        narrow, wide = (cols, rows) if axis == "x" else (rows, cols)
+        assert narrow.size == n, (axis, lo, hi, narrow)
+        if n:
+            first = int(np.ceil(np.float32(lo) - np.float32(0.5)))
+            assert narrow.tolist() == list(range(first, first + n))
+            assert wide.tolist() == list(range(20, 30))  # centres 20.5 .. 29.5
