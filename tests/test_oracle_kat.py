@@ -325,3 +325,53 @@ def test_pixel_centre_coverage_rules(ob, lo, hi, n):
             first = int(np.ceil(np.float32(lo) - np.float32(0.5)))
             assert narrow.tolist() == list(range(first, first + n))
             assert wide.tolist() == list(range(20, 30))  # centres 20.5 .. 29.5
+
+
+def _draw_all(ob, mb, cam, w, h, clear):
+    cfg = ob.default_frame_config(w, h)
+    cfg.clear_color = clear
+    color = np.full((h, w), clear, dtype=np.uint32)
+    depth = np.full((h, w), np.inf, dtype=np.float32)
+    for m in np.flatnonzero(mb.has_mesh).tolist():  # render_mesh per mesh, in chunk order, like the reference tests
+        ob.render_mesh(mb, m, cam.view_projection(), cfg, ob.default_atlas(), (0, 0, w, h), color, depth)
+    return int((color != clear).sum())
+
+
+def test_pipeline_pixel_count_thresholds(ob):
+    """tests/rendering_pipeline_tests.rs: the reference's own thresholds on drawn pixels, with the restated camera
+    (camera/mod.rs:20-61) and rasterizer."""
+    from differential_projection_voxel_renderer_b200 import camera, worldgen
+    # :17-57 render_single_voxel_writes_pixels: voxel (0,0,0), camera (32,32,80), 320x180, clear 0xFF000000 -> > 0
+    mb = ob.mesh_chunks(kat.chunk_single_voxel(0, 0, 0, kat.GRASS).reshape(1, -1), None, None, np.zeros((1, 3), np.int32))
+    assert _draw_all(ob, mb, camera.Camera((32.0, 32.0, 80.0), 320 / 180), 320, 180, 0xFF000000) > 0
+    # :185-260 near voxel (chunk 0,0,0) + voxel in chunk (0,0,6), camera (16,16,50), 640x360 -> >= 50
+    vox = np.stack([kat.chunk_single_voxel(16, 16, 16, kat.GRASS), kat.chunk_single_voxel(16, 16, 16, kat.STONE)])
+    pos = np.array([[0, 0, 0], [0, 0, 6]], dtype=np.int32)
+    mb = ob.mesh_chunks(vox, None, None, pos)
+    assert _draw_all(ob, mb, camera.Camera((16.0, 16.0, 50.0), 640 / 360), 640, 360, 0xFF000000) >= 50
+    # :263-311 a voxel in chunk (0,0,30) only (behind the -Z looking camera / sub-pixel) -> < 10
+    mb = ob.mesh_chunks(kat.chunk_single_voxel(16, 16, 16, kat.STONE).reshape(1, -1), None, None, np.array([[0, 0, 30]], np.int32))
+    assert _draw_all(ob, mb, camera.Camera((16.0, 16.0, 50.0), 640 / 360), 640, 360, 0xFF000000) < 10
+    # :314-360 close geometry: camera (16,16,20), voxel (16,16,16) -> > 1000
+    mb = ob.mesh_chunks(kat.chunk_single_voxel(16, 16, 16, kat.GRASS).reshape(1, -1), None, None, np.zeros((1, 3), np.int32))
+    assert _draw_all(ob, mb, camera.Camera((16.0, 16.0, 20.0), 640 / 360), 640, 360, 0xFF000000) > 1000
+    # :129-182 render_small_world_smoke_test: 3x3x3 terrain chunks, camera (32,32,80), 640x360 -> > 0
+    grid = np.array([[x, y, z] for x in (-1, 0, 1) for y in (-1, 0, 1) for z in (-1, 0, 1)], dtype=np.int32)
+    world = worldgen.generate_world(grid, store_uniform_voxels=True)
+    mb = ob.mesh_chunks(world.voxels, world.neighbor_table(), world.uniform_flags, world.positions)
+    assert _draw_all(ob, mb, camera.Camera((32.0, 32.0, 80.0), 640 / 360), 640, 360, 0xFF87CEEB) > 0
+
+
+def test_face_basis_backface_sign_and_slices(ob):
+    """tests/differential_projection_tests.rs:406-453: +Z / -Z basis normals have opposite z signs for a camera on +Z
+    looking at the origin; with the identity matrix the origin of a +Y basis moves with the slice, tangent and bitangent
+    do not."""
+    from differential_projection_voxel_renderer_b200 import camera
+    vp = camera.mat4_mul(camera.perspective_rh(np.radians(70.0), 16 / 9, 0.1, 1000.0),
+                         camera.look_at_rh((0, 0, 10), (0, 0, 0), (0, 1, 0))).reshape(16)
+    front, back = ob.face_basis(4, (0, 0, 0), 0, vp), ob.face_basis(5, (0, 0, 0), 0, vp)
+    assert np.sign(front[3][2]) != np.sign(back[3][2])
+    ident = np.eye(4, dtype=np.float32).reshape(16)
+    b0, b15, b31 = (ob.face_basis(2, (0, 0, 0), s, ident) for s in (0, 15, 31))
+    assert abs(b0[0][1] - 0.0) < 1e-3 and abs(b15[0][1] - 15.0) < 1e-3 and abs(b31[0][1] - 31.0) < 1e-3
+    assert np.array_equal(b0[1], b15[1]) and np.array_equal(b0[2], b31[2])
