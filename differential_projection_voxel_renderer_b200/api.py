@@ -452,6 +452,41 @@ def render_frame(batch: MeshBatch, view_proj, camera_position, cfg: VxFrameConfi
     return color_out, depth_out, (surv[:ns.value] if survivors_out is not None else surv[:ns.value].copy())
 
 
+class FrameLoop:
+    """The state main.rs keeps across iterations of its frame loop -- framebuffer, depth buffer, draw list
+    (main.rs:283-297, :379-608) -- bound once, so a frame costs one C-ABI call (vx_render_frame) and nothing else:
+    the ARGB frame (and depth, if asked for) lands in device-mapped page-locked host arrays written by the raster
+    kernel in place.  render() returns views of those arrays, valid until the next render()."""
+
+    def __init__(self, batch: MeshBatch, cfg: VxFrameConfig, view_distance: int = 0, want_depth: bool = False,
+                 ctx: Optional[Context] = None):
+        self.ctx = ctx or batch.ctx
+        self.batch = batch
+        self.cfg = cfg
+        rows = cfg.stripe_rows if cfg.stripe_rows > 0 else cfg.height
+        self.color = self.ctx.host_array((rows, cfg.width), np.uint32)
+        self.depth = self.ctx.host_array((rows, cfg.width), np.float32) if want_depth else None
+        if batch._n_chunks is None:
+            batch._n_chunks = int(batch.info().n_chunks)
+        self.survivors = np.empty(max(1, batch._n_chunks), dtype=np.int32)
+        self._vp = np.zeros(16, dtype=np.float32)
+        self._cam = np.zeros(3, dtype=np.float32)
+        self._ns = C.c_int32(0)
+        self._fn = self.ctx.lib.vx_render_frame
+        self._args = (self.ctx.handle, batch.handle, None, -1, self._vp.ctypes.data, self._cam.ctypes.data, int(view_distance),
+                      C.byref(cfg), self.color.ctypes.data, self.depth.ctypes.data if want_depth else None,
+                      self.survivors.ctypes.data, C.byref(self._ns))
+
+    def render(self, view_proj, camera_position):
+        """One frame: returns (color, depth or None, survivors) like render_frame."""
+        self._vp[:] = np.asarray(view_proj, dtype=np.float32).reshape(16)
+        self._cam[:] = camera_position
+        rc = self._fn(*self._args)
+        if rc != 0:
+            self.ctx.check(rc)
+        return self.color, self.depth, self.survivors[:self._ns.value]
+
+
 def render_frame_device(batch: MeshBatch, view_proj, camera_position, cfg: VxFrameConfig, view_distance: int,
                         ctx: Optional[Context] = None):
     """Device-resident frame: filter A on the device over the batch's chunks, nothing copied back."""

@@ -318,6 +318,26 @@ def test_mapped_host_framebuffer_is_written_in_place(ctx, ob, scene5):
     assert np.array_equal(color, oc) and np.array_equal(d.view(np.uint32), od.view(np.uint32))
 
 
+def test_frame_loop_moving_camera_matches_the_oracle_every_frame(ctx, ob, scene5):
+    """api.FrameLoop (framebuffer, depth buffer and draw list bound once, as main.rs:283-297 keeps them across the
+    loop): four camera poses in a row through the same bound buffers, every frame bit-identical to the oracle."""
+    _, p, batch, ref = scene5
+    w, h = 640, 360
+    cfg = api.default_frame_config(w, h)
+    loop = api.FrameLoop(batch, cfg, view_distance=5, want_depth=True, ctx=ctx)
+    for k in range(4):
+        cam = vx_scenes.path_camera(k, w, h)
+        vp, ids, oc, od, osurv = oracle_frame(ob, ref, p, cam, w, h, 5)
+        color, depth, surv = loop.render(vp, cam.position)
+        assert color is loop.color and depth is loop.depth
+        assert np.array_equal(surv, osurv)
+        assert np.array_equal(color, oc) and np.array_equal(depth.view(np.uint32), od.view(np.uint32))
+    # colour-only loop: no depth buffer is produced on the host
+    loop2 = api.FrameLoop(batch, cfg, view_distance=5, ctx=ctx)
+    color, depth, surv = loop2.render(vp, cam.position)
+    assert depth is None and np.array_equal(color, oc) and np.array_equal(surv, osurv)
+
+
 def test_full_size_frame_3840x2160_vd32_and_its_eight_stripes(ctx, ob):
     """BASELINE cfg 5: 3840x2160, view distance 32 (137,065 lattice chunks, ~5.9 k Varied), camera (0,10,20); the full
     frame and the eight 270-row stripes of the multi-GPU raster split, all bit-identical to the oracle."""
