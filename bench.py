@@ -610,6 +610,65 @@ def run_cuda(args):
         except Exception as e:
             gen_mesh = {"error": repr(e)}
 
+    # ---- adjacent rasterizers: the reference's own span-walker bench case and the macrotile frame ---
+    a18 = None
+    if world_size == 1:
+        try:
+            from oracle import binding as ob18
+            sw_w, sw_h = 1920, 1080  # benches/span_walker.rs:36-77 "span_walker_full_packet_32_quads": a 4 x 8 grid of quads
+            ii = np.arange(32)
+            bx0 = (np.float32(-0.9) + (ii % 8).astype(np.float32) * np.float32(0.225)).astype(np.float32)
+            by0 = (np.float32(-0.9) + (ii // 8).astype(np.float32) * np.float32(0.45)).astype(np.float32)
+            bx1 = (bx0 + np.float32(0.2)).astype(np.float32)
+            by1 = (by0 + np.float32(0.4)).astype(np.float32)
+            bz = np.full(32, 0.5, dtype=np.float32)
+            bt = ((ii % 4) + 1).astype(np.uint8)
+            d_boxes = torch.from_numpy(np.concatenate([bx0, by0, bx1, by1, bz])).to(dev)
+            d_types = torch.from_numpy(np.concatenate([bt, np.ones(32, dtype=np.uint8)])).to(dev)
+            d_col = torch.zeros((sw_h, sw_w), dtype=torch.int32, device=dev)
+            d_dep = torch.full((sw_h, sw_w), float("inf"), dtype=torch.float32, device=dev)
+
+            def walk():
+                ctx.check(ctx.lib.vx_span_walk_quads_device(ctx.handle, C.c_void_p(d_boxes.data_ptr()), C.c_void_p(d_types.data_ptr()), 32, sw_w, sw_h,
+                                                            C.c_void_p(d_col.data_ptr()), C.c_void_p(d_dep.data_ptr())))
+
+            walk()  # first call draws; the repeats below re-test equal depths like the reference's bench loop does
+            ctx.synchronize()
+            oc18 = np.zeros((sw_h, sw_w), dtype=np.uint32)
+            od18 = np.full((sw_h, sw_w), np.inf, dtype=np.float32)
+            ob18.span_walk_quads(oc18, od18, bx0, by0, bx1, by1, bz, bt)
+            same18 = bool(np.array_equal(d_col.cpu().numpy().view(np.uint32), oc18))
+            sw_ms = []
+            for _ in range(10):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                walk()
+                b.record(stream)
+                torch.cuda.synchronize()
+                sw_ms.append(a.elapsed_time(b))
+            t0 = time.perf_counter()
+            for _ in range(5):
+                ob18.span_walk_quads(oc18, od18, bx0, by0, bx1, by1, bz, bt)
+            sw_cpu_ms = (time.perf_counter() - t0) / 5 * 1e3
+            # macrotile frame of the headline scene: caller's list = every meshed chunk that passes filter A
+            vis18 = api.get_visible_chunks_frustum(p, cam.position, vp, VD, True, ctx)
+            ids18 = np.flatnonzero((vis18 != 0) & (qc_all > 0)).astype(np.int32)
+            cfg_m = api.VxFrameConfig.from_buffer_copy(cfg)
+            cfg_m.macrotile = 1
+            cfg_m.async_submit = 0
+            mt_ms = []
+            api.render_frame(batch, vp, cam.position, cfg_m, mesh_ids=ids18, ctx=ctx)
+            for _ in range(10):
+                t0 = time.perf_counter()
+                api.render_frame(batch, vp, cam.position, cfg_m, mesh_ids=ids18, want_depth=False, color_out=loop.color, ctx=ctx)
+                mt_ms.append((time.perf_counter() - t0) * 1e3)
+            a18 = {"span_walker_full_packet_32_quads_1920x1080_ms": float(np.median(sw_ms)), "span_walker_cpu_port_ms": sw_cpu_ms,
+                   "span_walker_matches_oracle": same18, "span_walker_launches": 5,
+                   "macrotile_frame_1280x720_vd12_e2e_ms": float(np.median(mt_ms)), "macrotile_meshes": int(ids18.size),
+                   "note": "vx_span_walk_quads_device (benches/span_walker.rs:36-77 workload, framebuffer resident) and vx_render_frame with cfg.macrotile = 1 (render_frame_macrotile) through the host API into mapped host memory, wall clock"}
+        except Exception as e:  # noqa: BLE001
+            a18 = {"error": repr(e)}
+
     # ---- BASELINE cfg 5 on this one GPU (context for the multi-GPU design point): 3840x2160, view distance 32 ------------
     cfg5 = None
     if world_size == 1:
@@ -690,6 +749,7 @@ def run_cuda(args):
             "mesh_e2e_steady_state": mesh_e2e,
             "e2e_double_buffered_frames_per_s": round(e2e_pipelined, 1) if e2e_pipelined else None,
             "generate_and_mesh_on_device": gen_mesh,
+            "adjacent_rasterizers_a18": a18,
             "frames_per_sec_alternate_frame_rendering": afr_fps,
             "alternate_frame_rendering": "N > 1 only: every GPU renders whole 1280x720 frames independently (no collective), total frames / max time over ranks; the headline value is the stripe-sharded single frame (strong scaling)",
             "reference_published": "162-168 fps on a 6-core i5-12400 (README.md:29-32)",

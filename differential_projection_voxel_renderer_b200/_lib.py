@@ -41,7 +41,7 @@ class VxFrameConfig(C.Structure):
                 ("light_dir", C.c_float * 3), ("ambient", C.c_float), ("diffuse", C.c_float),
                 ("stripe_y0", C.c_int32), ("stripe_rows", C.c_int32),
                 ("differential_projection", C.c_int32), ("async_submit", C.c_int32),
-                ("profile_kernels", C.c_int32), ("reserved", C.c_int32 * 1)]
+                ("profile_kernels", C.c_int32), ("macrotile", C.c_int32)]
 
 
 class VxTerrainParams(C.Structure):
@@ -100,6 +100,10 @@ PROTOTYPES = {
     "vx_default_atlas": (None, [C.POINTER(VxAtlas)]),
     "vx_set_atlas": (C.c_int, [_P, C.POINTER(VxAtlas)]),
     "vx_render_frame": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig), _P, _P, _P, C.POINTER(_I)]),
+    "vx_render_frame_macrotile": (C.c_int, [_P, _P, _P, _I, _P, C.POINTER(VxFrameConfig), _P, _P, _P, C.POINTER(_I)]),
+    "vx_span_walk_quads": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "vx_span_walk_quads_device": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "vx_fill_spans": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "vx_render_frame_device": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig)]),
     "vx_render_frame_into": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig), _P, _P]),
     "vx_framebuffer_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I), C.POINTER(_I)]),

@@ -384,6 +384,46 @@ class Framebuffer:
         self.color_buffer[...] = np.uint32(clear_color)
         self.depth_buffer[...] = np.inf
 
+    def fill_spans(self, y, x_start, x_end, depth, color, ctx: Optional[Context] = None):
+        """FrameSlice::fill_span (span_walker.rs:412-441) for n spans in order: pixels [x_start, x_end) of row y, depth test `<`."""
+        ctx = ctx or default_context()
+        ya, xs, xe = (np.ascontiguousarray(a, dtype=np.int32).ravel() for a in (y, x_start, x_end))
+        d = np.ascontiguousarray(depth, dtype=np.float32).ravel()
+        c = np.ascontiguousarray(color, dtype=np.uint32).ravel()
+        if not (ya.size == xs.size == xe.size == d.size == c.size):
+            raise ValueError("fill_spans: arrays of different length")
+        ctx.check(ctx.lib.vx_fill_spans(ctx.handle, _p(ya), _p(xs), _p(xe), _p(d), _p(c), int(ya.size), self.width, self.height,
+                                        _p(self.color_buffer), _p(self.depth_buffer)))
+
+    def fill_span(self, y: int, x_start: int, x_end: int, depth: float, color: int, ctx: Optional[Context] = None):
+        self.fill_spans([y], [x_start], [x_end], [depth], [color], ctx)
+
+
+class SpanWalkerRasterizer:
+    """span_walker.rs:97-396: flat-colour rasterizer of projected axis-aligned quads (the Hyper-Pipeline's last stage)."""
+
+    BLOCK_COLORS = (0x00000000, 0x00FF00FF, 0x8B4513FF, 0x808080FF)  # get_block_color :386-396
+
+    def __init__(self, viewport_width: int, viewport_height: int, ctx: Optional[Context] = None):
+        self.viewport_width = int(viewport_width)
+        self.viewport_height = int(viewport_height)
+        self.ctx = ctx or default_context()
+
+    def rasterize_projected_packet(self, x_min, y_min, x_max, y_max, depth_near, block_type, framebuffer: Framebuffer, visible=None):
+        """rasterize_projected_packet :116 for n quads (any number of ProjectedPackets concatenated; `visible` = the bits
+        of their visibility masks, None = all).  The framebuffer must have the walker's viewport size."""
+        if (framebuffer.width, framebuffer.height) != (self.viewport_width, self.viewport_height):
+            raise ValueError("framebuffer and viewport sizes differ")
+        f = [np.ascontiguousarray(a, dtype=np.float32).ravel() for a in (x_min, y_min, x_max, y_max, depth_near)]
+        bt = np.ascontiguousarray(block_type, dtype=np.uint8).ravel()
+        vis = None if visible is None else np.ascontiguousarray(visible, dtype=np.uint8).ravel()
+        n = int(bt.size)
+        if any(a.size != n for a in f) or (vis is not None and vis.size != n):
+            raise ValueError("rasterize_projected_packet: arrays of different length")
+        self.ctx.check(self.ctx.lib.vx_span_walk_quads(self.ctx.handle, _p(f[0]), _p(f[1]), _p(f[2]), _p(f[3]), _p(f[4]), _p(bt), _p(vis), n,
+                                                       framebuffer.width, framebuffer.height, _p(framebuffer.color_buffer),
+                                                       _p(framebuffer.depth_buffer)))
+
 
 class Rasterizer:
     """rasterizer.rs:335-431.  pub fields: backface_culling, enable_shading, shading (via frame config), atlas."""
@@ -450,6 +490,22 @@ def render_frame(batch: MeshBatch, view_proj, camera_position, cfg: VxFrameConfi
     ctx.check(ctx.lib.vx_render_frame(ctx.handle, batch.handle, _p(mesh_ids), n, _p(vp), _p(cam), int(view_distance), C.byref(cfg),
                                       _p(color_out), _p(depth_out), _p(surv), C.byref(ns)))
     return color_out, depth_out, (surv[:ns.value] if survivors_out is not None else surv[:ns.value].copy())
+
+
+def render_frame_macrotile(batch: MeshBatch, mesh_ids, view_proj, cfg: VxFrameConfig, want_tile_depth: bool = True,
+                           ctx: Optional[Context] = None):
+    """render_frame_macrotile (macrotile_renderer.rs:51-170).  Returns (color (H,W) u32, tile depth (H,W) f32 or None --
+    the reference drops it --, projected mesh ids in draw order: list order, large primitives last)."""
+    ctx = ctx or batch.ctx
+    vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+    ids = np.ascontiguousarray(mesh_ids, dtype=np.int32).ravel()
+    color = np.empty((cfg.height, cfg.width), dtype=np.uint32)
+    depth = np.empty((cfg.height, cfg.width), dtype=np.float32) if want_tile_depth else None
+    proj = np.empty(max(1, ids.size), dtype=np.int32)
+    n = C.c_int32(0)
+    ctx.check(ctx.lib.vx_render_frame_macrotile(ctx.handle, batch.handle, _p(ids), int(ids.size), _p(vp), C.byref(cfg), _p(color), _p(depth),
+                                                _p(proj), C.byref(n)))
+    return color, depth, proj[:n.value].copy()
 
 
 class FrameLoop:

@@ -1,0 +1,272 @@
+// vx_spanwalk.cu -- the reference's flat-colour span walker on the device:
+//   SpanWalkerRasterizer::rasterize_projected_packet  span_walker.rs:116-283
+//   FrameSlice::fill_span                             span_walker.rs:412-441
+//
+// The reference walks quads one after the other, rows top to bottom, and depth-tests every pixel with `<`, so a
+// pixel ends up with the colour of the FIRST quad (submission order) among those of minimal depth that cover it.
+// Batching quads in groups of eight (TrapezoidBatch) only changes the order in which rows of different quads are
+// visited, never the order of two fragments of one pixel.  Here every fragment is a 64-bit key
+//   [ order-preserving depth : 32 | 1 + submission index : 32 ]
+// merged with atomicMin; the pixel's previous content enters as [depth | 0], which wins every tie exactly like
+// `depth < stored` loses it.  Four launches: setup (screen boxes + work count per quad), scan, fill, resolve.
+#include "vx_common.cuh"
+#include "vx_math.cuh"
+
+namespace {
+
+constexpr int SW_THREADS = 256;
+constexpr int SW_ROWS = 8;         // rows of one fill task
+constexpr int SW_SCAN_THREADS = 1024;
+
+struct SpanRec {
+    int32_t y0, y1;  // rows y0 .. y1 inclusive (y0 > y1: nothing)
+    int32_t xs, xe;  // columns [xs, xe)
+    float depth;
+    uint32_t color;
+};
+
+struct SpanCtl {
+    unsigned long long total_tasks;
+};
+
+__device__ __forceinline__ uint32_t block_color(uint8_t t) { // span_walker.rs:386-396, block_type.rs:70-78
+    return t == 1 ? 0x00FF00FFu : t == 2 ? 0x8B4513FFu : t == 3 ? 0x808080FFu : 0u;
+}
+
+// mode 0: projected quads (NDC boxes).  in_f = x_min, y_min, x_max, y_max, depth_near (n each); in_b = block type, visible
+// mode 1: explicit spans.               in_i = y, x_start, x_end (n each); in_f = depth; in_u = colour
+__global__ void __launch_bounds__(SW_THREADS) spanwalk_setup_kernel(int mode, const float *__restrict__ in_f, const uint8_t *__restrict__ in_b,
+                                                                  const int32_t *__restrict__ in_i, const uint32_t *__restrict__ in_u,
+                                                                  int n, int W, int H, SpanRec *__restrict__ recs, uint32_t *__restrict__ n_tasks) {
+    const int i = blockIdx.x * SW_THREADS + threadIdx.x;
+    if (i >= n) return;
+    SpanRec r;
+    r.y0 = 1; r.y1 = 0; r.xs = 0; r.xe = 0; r.depth = 0.0f; r.color = 0u;
+    const size_t N = (size_t)n;
+    if (mode == 0) {
+        const bool visible = in_b[N + i] != 0;
+        const float depth = in_f[4 * N + i];
+        if (visible) {
+            const float vp_w = (float)W, vp_h = (float)H;
+            const float EPSILON = 0.001f; // span_walker.rs:142
+            const float sx_min = fmaxf((in_f[i] + 1.0f) * 0.5f * vp_w, 0.0f);                       // :151
+            const float sy_min = fmaxf((1.0f - in_f[3 * N + i]) * 0.5f * vp_h, 0.0f);               // :152
+            const float sx_max = fminf((in_f[2 * N + i] + 1.0f) * 0.5f * vp_w + EPSILON, vp_w);     // :155
+            const float sy_max = fminf((1.0f - in_f[N + i]) * 0.5f * vp_h + EPSILON, vp_h);         // :156
+            const bool outside = sx_min >= vp_w || sy_min >= vp_h || sx_max <= 0.0f || sy_max <= 0.0f; // :159-165
+            if (!outside && depth == depth) { // a NaN depth never passes `depth < stored`
+                // rows whose centre lies in [sy_min, sy_max) (:237-247, update_active_mask :76-84), inside the frame
+                int ya = vx_f2i(ceilf(sy_min - 0.5f));
+                if (ya < 0) ya = 0;
+                while (ya > 0 && (float)(ya - 1) + 0.5f >= sy_min) --ya;
+                while (ya < H && (float)ya + 0.5f < sy_min) ++ya;
+                int yb = vx_f2i(ceilf(sy_max - 0.5f)) - 1;
+                if (yb > H - 1) yb = H - 1;
+                while (yb + 1 <= H - 1 && (float)(yb + 1) + 0.5f < sy_max) ++yb;
+                while (yb >= 0 && !((float)yb + 0.5f < sy_max)) --yb;
+                int xs = vx_f2i(roundf(sx_min)), xe = vx_f2i(roundf(sx_max)); // :253-254
+                xs = min(max(xs, 0), W - 1);                                    // fill_span :422-424
+                xe = min(max(xe, 0), W);
+                if (ya <= yb && xs < xe) {
+                    r.y0 = ya; r.y1 = yb; r.xs = xs; r.xe = xe;
+                }
+            }
+        }
+        r.depth = depth;
+        r.color = block_color(in_b[i]);
+    } else {
+        const int y = in_i[i];
+        int xs = in_i[N + i], xe = in_i[2 * N + i];
+        xs = min(max(xs, 0), W - 1);
+        xe = min(max(xe, 0), W);
+        r.depth = in_f[i];
+        r.color = in_u[i];
+        if (xs < xe && r.depth == r.depth) { // y is validated on the host
+            r.y0 = y; r.y1 = y; r.xs = xs; r.xe = xe;
+        }
+    }
+    recs[i] = r;
+    n_tasks[i] = r.y0 <= r.y1 ? (uint32_t)((r.y1 - r.y0) / SW_ROWS + 1) : 0u;
+}
+
+// exclusive prefix sum of n_tasks (one CTA; n is the number of quads of one call, not a per-frame hot loop)
+__global__ void __launch_bounds__(SW_SCAN_THREADS) spanwalk_scan_kernel(const uint32_t *__restrict__ n_tasks, int n, unsigned long long *__restrict__ task_base,
+                                                                       SpanCtl *ctl) {
+    __shared__ unsigned long long part[SW_SCAN_THREADS];
+    const int tid = threadIdx.x;
+    const int per = (n + SW_SCAN_THREADS - 1) / SW_SCAN_THREADS;
+    const int lo = min(tid * per, n), hi = min(lo + per, n);
+    unsigned long long s = 0;
+    for (int i = lo; i < hi; ++i) s += n_tasks[i];
+    part[tid] = s;
+    __syncthreads();
+    for (int o = 1; o < SW_SCAN_THREADS; o <<= 1) { // Hillis-Steele inclusive scan
+        unsigned long long v = tid >= o ? part[tid - o] : 0ull;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    unsigned long long run = part[tid] - s;
+    for (int i = lo; i < hi; ++i) {
+        task_base[i] = run;
+        run += n_tasks[i];
+    }
+    if (tid == SW_SCAN_THREADS - 1) ctl->total_tasks = part[tid];
+}
+
+__global__ void __launch_bounds__(SW_THREADS) spanwalk_init_keys_kernel(const float *__restrict__ depth, size_t npx, unsigned long long *__restrict__ keys) {
+    for (size_t p = (size_t)blockIdx.x * SW_THREADS + threadIdx.x; p < npx; p += (size_t)gridDim.x * SW_THREADS) {
+        const float d = depth[p];
+        // a stored NaN rejects every fragment (`x < NaN` is false): key 0 is below every fragment key
+        keys[p] = d == d ? ((unsigned long long)vx_ord(d + 0.0f) << 32) : 0ull;
+    }
+}
+
+// one warp per task = up to SW_ROWS rows of one quad; tasks are taken round-robin by a persistent grid
+__global__ void __launch_bounds__(SW_THREADS) spanwalk_fill_kernel(const SpanRec *__restrict__ recs, const unsigned long long *__restrict__ task_base,
+                                                                 int n, const SpanCtl *__restrict__ ctl, int W, unsigned long long *__restrict__ keys) {
+    const unsigned long long total = ctl->total_tasks;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * (SW_THREADS / 32);
+    for (unsigned long long t = (unsigned long long)blockIdx.x * (SW_THREADS / 32) + (threadIdx.x >> 5); t < total; t += n_warps) {
+        // owner of task t = the right-most record with task_base <= t: a record without tasks has the base of its
+        // successor, so it is never right-most among those <= t unless every later base is > t, and then its own is too
+        int lo = 0, hi = n - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (task_base[mid] <= t) lo = mid;
+            else hi = mid - 1;
+        }
+        const SpanRec r = recs[lo];
+        const int chunk = (int)(t - task_base[lo]);
+        const int ya = r.y0 + chunk * SW_ROWS, yb = min(ya + SW_ROWS - 1, r.y1);
+        const int w = r.xe - r.xs;
+        const unsigned long long key = ((unsigned long long)vx_ord(r.depth + 0.0f) << 32) | (unsigned long long)((uint32_t)lo + 1u);
+        const int count = (yb - ya + 1) * w;
+        for (int k = lane; k < count; k += 32) {
+            const int y = ya + k / w, x = r.xs + k % w;
+            atomicMin(&keys[(size_t)y * W + x], key);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SW_THREADS) spanwalk_resolve_kernel(const unsigned long long *__restrict__ keys, const SpanRec *__restrict__ recs, size_t npx,
+                                                                    uint32_t *__restrict__ color, float *__restrict__ depth) {
+    for (size_t p = (size_t)blockIdx.x * SW_THREADS + threadIdx.x; p < npx; p += (size_t)gridDim.x * SW_THREADS) {
+        const uint32_t seq = (uint32_t)keys[p];
+        if (seq) {
+            const SpanRec r = recs[seq - 1];
+            depth[p] = r.depth; // the quad's own bits (keeps a -0.0)
+            color[p] = r.color;
+        }
+    }
+}
+
+int span_walk_device(VxContext *ctx, int mode, const float *d_f, const uint8_t *d_b, const int32_t *d_i, const uint32_t *d_u, int32_t n,
+                     int32_t W, int32_t H, uint32_t *d_color, float *d_depth) {
+    const size_t npx = (size_t)W * (size_t)H;
+    // scratch: records | task counts | task bases | ctl | keys
+    const size_t N = (size_t)n;
+    const size_t off_cnt = (sizeof(SpanRec) * N + 255) & ~(size_t)255;
+    const size_t off_base = (off_cnt + 4 * N + 255) & ~(size_t)255;
+    const size_t off_ctl = (off_base + 8 * N + 255) & ~(size_t)255;
+    VX_CUDA(ctx, ctx->tmp_c.reserve(off_ctl + 256));
+    VX_CUDA(ctx, ctx->tmp_d.reserve(8 * npx));
+    char *base = ctx->tmp_c.as<char>();
+    SpanRec *recs = reinterpret_cast<SpanRec *>(base);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(base + off_cnt);
+    unsigned long long *tb = reinterpret_cast<unsigned long long *>(base + off_base);
+    SpanCtl *ctl = reinterpret_cast<SpanCtl *>(base + off_ctl);
+    unsigned long long *keys = ctx->tmp_d.as<unsigned long long>();
+    const size_t px_blocks = (npx + SW_THREADS - 1) / SW_THREADS, px_cap = (size_t)ctx->num_sms * 8;
+    const int px_grid = (int)(px_blocks < px_cap ? px_blocks : px_cap);
+    spanwalk_init_keys_kernel<<<px_grid, SW_THREADS, 0, ctx->stream>>>(d_depth, npx, keys);
+    VX_CHECK_LAUNCH(ctx);
+    spanwalk_setup_kernel<<<(n + SW_THREADS - 1) / SW_THREADS, SW_THREADS, 0, ctx->stream>>>(mode, d_f, d_b, d_i, d_u, n, W, H, recs, cnt);
+    VX_CHECK_LAUNCH(ctx);
+    spanwalk_scan_kernel<<<1, SW_SCAN_THREADS, 0, ctx->stream>>>(cnt, n, tb, ctl);
+    VX_CHECK_LAUNCH(ctx);
+    spanwalk_fill_kernel<<<ctx->num_sms * 8, SW_THREADS, 0, ctx->stream>>>(recs, tb, n, ctl, W, keys);
+    VX_CHECK_LAUNCH(ctx);
+    spanwalk_resolve_kernel<<<px_grid, SW_THREADS, 0, ctx->stream>>>(keys, recs, npx, d_color, d_depth);
+    VX_CHECK_LAUNCH(ctx);
+    return VX_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int vx_span_walk_quads_device(VxContext *ctx, const float *d_boxes, const uint8_t *d_types, int32_t n, int32_t width, int32_t height,
+                              uint32_t *d_color, float *d_depth) {
+    if (!ctx || n < 0 || width <= 0 || height <= 0 || !d_color || !d_depth || (n > 0 && (!d_boxes || !d_types)))
+        return vx_fail(ctx, VX_ERR_INVALID, "vx_span_walk_quads_device: bad argument");
+    if (n == 0) return VX_OK;
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    return span_walk_device(ctx, 0, d_boxes, d_types, nullptr, nullptr, n, width, height, d_color, d_depth);
+}
+
+int vx_span_walk_quads(VxContext *ctx, const float *x_min, const float *y_min, const float *x_max, const float *y_max,
+                       const float *depth_near, const uint8_t *block_type, const uint8_t *visible, int32_t n, int32_t width,
+                       int32_t height, uint32_t *color_inout, float *depth_inout) {
+    if (!ctx || n < 0 || width <= 0 || height <= 0 || !color_inout || !depth_inout)
+        return vx_fail(ctx, VX_ERR_INVALID, "vx_span_walk_quads: bad argument");
+    if (n == 0) return VX_OK;
+    if (!x_min || !y_min || !x_max || !y_max || !depth_near || !block_type) return vx_fail(ctx, VX_ERR_INVALID, "vx_span_walk_quads: null array");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t N = (size_t)n, npx = (size_t)width * (size_t)height;
+    const size_t off_b = (20 * N + 255) & ~(size_t)255;
+    VX_CUDA(ctx, ctx->tmp_a.reserve(off_b + 2 * N));
+    VX_CUDA(ctx, ctx->tmp_b.reserve(8 * npx));
+    float *d_f = ctx->tmp_a.as<float>();
+    uint8_t *d_b = ctx->tmp_a.as<uint8_t>() + off_b;
+    const float *src[5] = {x_min, y_min, x_max, y_max, depth_near};
+    for (int k = 0; k < 5; ++k) VX_CUDA(ctx, cudaMemcpyAsync(d_f + k * N, src[k], 4 * N, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(d_b, block_type, N, cudaMemcpyHostToDevice, ctx->stream));
+    if (visible) VX_CUDA(ctx, cudaMemcpyAsync(d_b + N, visible, N, cudaMemcpyHostToDevice, ctx->stream));
+    else VX_CUDA(ctx, cudaMemsetAsync(d_b + N, 1, N, ctx->stream));
+    uint32_t *d_color = ctx->tmp_b.as<uint32_t>();
+    float *d_depth = reinterpret_cast<float *>(d_color + npx);
+    VX_CUDA(ctx, cudaMemcpyAsync(d_color, color_inout, 4 * npx, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(d_depth, depth_inout, 4 * npx, cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = span_walk_device(ctx, 0, d_f, d_b, nullptr, nullptr, n, width, height, d_color, d_depth);
+    if (rc != VX_OK) return rc;
+    VX_CUDA(ctx, cudaMemcpyAsync(color_inout, d_color, 4 * npx, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(depth_inout, d_depth, 4 * npx, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+int vx_fill_spans(VxContext *ctx, const int32_t *y, const int32_t *x_start, const int32_t *x_end, const float *depth,
+                  const uint32_t *color, int32_t n, int32_t width, int32_t height, uint32_t *color_inout, float *depth_inout) {
+    if (!ctx || n < 0 || width <= 0 || height <= 0 || !color_inout || !depth_inout)
+        return vx_fail(ctx, VX_ERR_INVALID, "vx_fill_spans: bad argument");
+    if (n == 0) return VX_OK;
+    if (!y || !x_start || !x_end || !depth || !color) return vx_fail(ctx, VX_ERR_INVALID, "vx_fill_spans: null array");
+    for (int32_t i = 0; i < n; ++i) // the reference indexes row y unchecked and would panic
+        if (y[i] < 0 || y[i] >= height) return vx_fail(ctx, VX_ERR_INVALID, "vx_fill_spans: row outside the framebuffer");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t N = (size_t)n, npx = (size_t)width * (size_t)height;
+    VX_CUDA(ctx, ctx->tmp_a.reserve(20 * N));
+    VX_CUDA(ctx, ctx->tmp_b.reserve(8 * npx));
+    int32_t *d_i = ctx->tmp_a.as<int32_t>();
+    float *d_f = reinterpret_cast<float *>(d_i + 3 * N);
+    uint32_t *d_u = reinterpret_cast<uint32_t *>(d_i + 4 * N);
+    VX_CUDA(ctx, cudaMemcpyAsync(d_i, y, 4 * N, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(d_i + N, x_start, 4 * N, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(d_i + 2 * N, x_end, 4 * N, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(d_f, depth, 4 * N, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(d_u, color, 4 * N, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t *d_color = ctx->tmp_b.as<uint32_t>();
+    float *d_depth = reinterpret_cast<float *>(d_color + npx);
+    VX_CUDA(ctx, cudaMemcpyAsync(d_color, color_inout, 4 * npx, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(d_depth, depth_inout, 4 * npx, cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = span_walk_device(ctx, 1, d_f, nullptr, d_i, d_u, n, width, height, d_color, d_depth);
+    if (rc != VX_OK) return rc;
+    VX_CUDA(ctx, cudaMemcpyAsync(color_inout, d_color, 4 * npx, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(depth_inout, d_depth, 4 * npx, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+} // extern "C"

@@ -93,7 +93,12 @@ typedef struct {
      * durations with vx_frame_kernel_times().  2: additionally record the raster work-item timeline
      * (vx_frame_trace). */
     int32_t profile_kernels;
-    int32_t reserved[1];
+    /* 1: render_frame_macrotile semantics (macrotile_renderer.rs:51-170, macrotile.rs:179-224): no near-depth sort --
+     * meshes are drawn in list order, those whose screen box covers more than 25 % of the frame (large primitives)
+     * after all others -- and every 128-pixel macrotile column is its own PixelTarget, i.e. a span's interpolation
+     * restarts at the column's first pixel (rasterizer.rs:1404-1432 with rect_x0 = the tile's x0).
+     * profile_kernels = 2 acts like 1 in this mode. */
+    int32_t macrotile;
 } VxFrameConfig;
 
 typedef struct {
@@ -277,6 +282,40 @@ VX_API int vx_frame_trace(VxContext *ctx, uint64_t *out, int32_t cap_items, int3
 VX_API int vx_frame_setup_trace(VxContext *ctx, uint64_t *out, int32_t cap_ctas, int32_t *n_ctas);
 /* Diagnostics: triangles binned per 128x8 tile in the last frame (row-major tile grid, ntx x nty). */
 VX_API int vx_frame_bin_counts(VxContext *ctx, uint32_t *counts_out, int32_t cap, int32_t *ntx, int32_t *nty);
+
+/* render_frame_macrotile (macrotile_renderer.rs:51-170; MacroTileBins::add_mesh macrotile.rs:179-224, MacroTile as
+ * PixelTarget :300-343): clear, project_mesh_aabb per mesh of the caller's list (:175-250, the arithmetic of filter B),
+ * per 128x128 macrotile the binned meshes in list order and then the large primitives (> 25 % of the screen) through
+ * the span rasterizer with the tile as target, tile colours flushed to color_out (W x H).  = vx_render_frame with
+ * cfg.macrotile = 1 and no distance / near-depth sort.  tile_depth_out (W x H, may be NULL) receives the tiles' depth
+ * buffers, which the reference drops (its framebuffer depth stays +inf).  projected_out (n_meshes entries, may be
+ * NULL): the meshes that passed project_mesh_aabb in draw order -- list order, large primitives last;
+ * *n_projected = the reference's return value.  The Hi-Z buffer argument of the reference is only cleared there
+ * and never consulted, so it has no counterpart.  A mesh is assumed to stay inside its projected chunk box (the
+ * reference bins by that box; geometry of a chunk cannot leave it). */
+VX_API int vx_render_frame_macrotile(VxContext *ctx, const VxMeshBatch *batch, const int32_t *mesh_ids, int32_t n_meshes,
+                              const float vp[16], const VxFrameConfig *cfg, uint32_t *color_out, float *tile_depth_out,
+                              int32_t *projected_out, int32_t *n_projected);
+
+/* SpanWalkerRasterizer::rasterize_projected_packet (span_walker.rs:116-283) + FrameSlice::fill_span (:412-441) over n
+ * projected quads in submission order (ProjectedPackets concatenated, differential_projection.rs:295-304: NDC boxes,
+ * constant depth, block type; visible[i] = bit i of visibility_mask, NULL = all visible): rows whose centre lies in
+ * the screen box, columns round(x_min) .. round(x_max + 0.001), flat colour per block type (:386-396), depth test
+ * `<` against the existing contents of the W x H host framebuffer (read-modify-write).  The viewport of the walker
+ * and the framebuffer have the same size, as everywhere in the reference. */
+VX_API int vx_span_walk_quads(VxContext *ctx, const float *x_min, const float *y_min, const float *x_max, const float *y_max,
+                       const float *depth_near, const uint8_t *block_type, const uint8_t *visible, int32_t n, int32_t width,
+                       int32_t height, uint32_t *color_inout, float *depth_inout);
+/* Same on device-resident data: d_boxes = x_min[n], y_min[n], x_max[n], y_max[n], depth_near[n]; d_types =
+ * block_type[n], visible[n]; d_color / d_depth = W x H framebuffer in device memory.  Asynchronous on the context's
+ * stream. */
+VX_API int vx_span_walk_quads_device(VxContext *ctx, const float *d_boxes, const uint8_t *d_types, int32_t n, int32_t width,
+                              int32_t height, uint32_t *d_color, float *d_depth);
+/* FrameSlice::fill_span (span_walker.rs:412-441) for n spans in submission order: pixels [x_start, x_end) of row y
+ * after the reference's clamps, depth test `<`.  A row outside the framebuffer is VX_ERR_INVALID (the reference
+ * would index out of bounds). */
+VX_API int vx_fill_spans(VxContext *ctx, const int32_t *y, const int32_t *x_start, const int32_t *x_end, const float *depth,
+                  const uint32_t *color, int32_t n, int32_t width, int32_t height, uint32_t *color_inout, float *depth_inout);
 
 /* Rasterizer::render_mesh / render_mesh_into_slice / render_mesh_into_tile (rasterizer.rs:385-431)
  * for one mesh into a caller framebuffer (W x H host arrays, read-modify-write: depth-tested against

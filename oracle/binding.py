@@ -270,3 +270,62 @@ def quad_clip_vertices(face, slice_pos, u, v, w, h, chunk_pos, vp) -> np.ndarray
     lib().vxo_quad_clip_vertices(C.c_int(face), C.c_uint8(slice_pos), C.c_uint8(u), C.c_uint8(v), C.c_uint8(w),
                                  C.c_uint8(h), _p(cp), _p(vp), _p(out))
     return out
+
+
+# ---- adjacent rasterizers -----------------------------------------------------------------
+
+def span_walker_block_color(block_type: int) -> int:
+    f = lib().vxo_span_walker_block_color
+    f.restype = C.c_uint32
+    return int(f(C.c_uint8(block_type)))
+
+
+def fill_span(color, depth, y, x_start, x_end, d, c):
+    """FrameSlice::fill_span on (H, W) colour / depth arrays, in place."""
+    lib().vxo_fill_span(C.c_int32(color.shape[1]), C.c_int32(y), C.c_int32(x_start), C.c_int32(x_end), C.c_float(d),
+                        C.c_uint32(c), _p(color), _p(depth))
+
+
+def span_walk_quads(color, depth, x_min, y_min, x_max, y_max, depth_near, block_type, visible=None):
+    """SpanWalkerRasterizer::rasterize_projected_packet over n projected quads submitted as consecutive
+    ProjectedPackets of up to 32 (the layout PacketPipeline produces), in place on (H, W) colour / depth arrays."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float32).ravel() for a in (x_min, y_min, x_max, y_max, depth_near)]
+    bt = np.ascontiguousarray(block_type, dtype=np.uint8).ravel()
+    n = bt.size
+    vis = np.ones(n, dtype=np.uint8) if visible is None else np.ascontiguousarray(visible, dtype=np.uint8).ravel()
+    h, w = color.shape
+    for p0 in range(0, n, 32):
+        cnt = min(32, n - p0)
+        mask = 0
+        for i in range(cnt):
+            if vis[p0 + i]:
+                mask |= 1 << i
+        sl = [np.ascontiguousarray(a[p0:p0 + cnt]) for a in arrs]
+        b = np.ascontiguousarray(bt[p0:p0 + cnt])
+        lib().vxo_span_walk_packet(_p(sl[0]), _p(sl[1]), _p(sl[2]), _p(sl[3]), _p(sl[4]), _p(b), C.c_uint32(mask),
+                                   C.c_int32(cnt), C.c_int32(w), C.c_int32(h), _p(color), _p(depth))
+
+
+def macrotile_bin(min_x, min_y, max_x, max_y, fb_w, fb_h):
+    """MacroTileBins::add_mesh: (kind, (tx0, ty0, tx1, ty1)); kind 1 binned, 2 large primitive, 0 off-screen."""
+    t = np.zeros(4, dtype=np.int32)
+    k = lib().vxo_macrotile_bin(C.c_int32(min_x), C.c_int32(min_y), C.c_int32(max_x), C.c_int32(max_y), C.c_int32(fb_w),
+                                C.c_int32(fb_h), _p(t))
+    return int(k), tuple(int(x) for x in t)
+
+
+def render_frame_macrotile(mb: MeshBatch, mesh_ids, vp, cfg: FrameConfig, atlas: Atlas, want_kinds: bool = False):
+    """render_frame_macrotile: returns (color (H,W) u32, tile depth (H,W) f32 [diagnostic], projected mesh ids in list
+    order[, kind per projected mesh: 1 binned, 2 large primitive])."""
+    mesh_ids = np.ascontiguousarray(mesh_ids, dtype=np.int32)
+    vp = np.ascontiguousarray(vp, dtype=np.float32).reshape(16)
+    color = np.zeros((cfg.height, cfg.width), dtype=np.uint32)
+    depth = np.zeros((cfg.height, cfg.width), dtype=np.float32)
+    proj = np.zeros(max(1, mesh_ids.shape[0]), dtype=np.int32)
+    kind = np.zeros(max(1, mesh_ids.shape[0]), dtype=np.int32)
+    v = mb.view()
+    k = lib().vxo_render_frame_macrotile(C.byref(v), _p(mesh_ids), C.c_int32(mesh_ids.shape[0]), _p(vp), C.byref(cfg),
+                                         C.byref(atlas), _p(color), _p(depth), _p(proj), _p(kind))
+    if want_kinds:
+        return color, depth, proj[:k].copy(), kind[:k].copy()
+    return color, depth, proj[:k].copy()

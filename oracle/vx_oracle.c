@@ -910,3 +910,217 @@ void vxo_transform_vertices(const uint8_t *verts, int32_t n, const float offset[
         mat4_mul_vec4(vp, offset[0] + (float)v[0], offset[1] + (float)v[1], offset[2] + (float)v[2], 1.0f, out4 + 4 * (size_t)i);
     }
 }
+
+/* ---------- adjacent rasterizers -------------------- */
+
+/* SpanWalkerRasterizer::get_block_color span_walker.rs:386-396 (BlockType::from_u8 block_type.rs:70-78) */
+uint32_t vxo_span_walker_block_color(uint8_t block_type) {
+    switch (block_type) {
+    case 1: return 0x00FF00FFu;
+    case 2: return 0x8B4513FFu;
+    case 3: return 0x808080FFu;
+    default: return 0x00000000u;
+    }
+}
+
+/* FrameSlice::fill_span span_walker.rs:412-441 on a full-frame slice of `width` columns. */
+void vxo_fill_span(int32_t width, int32_t y, int32_t x_start, int32_t x_end, float depth, uint32_t color,
+                   uint32_t *cbuf, float *dbuf) {
+    x_start = imin(imax(x_start, 0), width - 1);
+    x_end = imin(imax(x_end, 0), width);
+    if (x_start >= x_end) return;
+    size_t row = (size_t)y * (size_t)width;
+    for (int32_t x = x_start; x < x_end; ++x) {
+        size_t idx = row + (size_t)x;
+        if (depth < dbuf[idx]) {
+            dbuf[idx] = depth;
+            cbuf[idx] = color;
+        }
+    }
+}
+
+typedef struct { /* TrapezoidBatch span_walker.rs:20-52 */
+    int count;
+    float left_x[8], right_x[8], left_slope[8], right_slope[8], start_y[8], end_y[8], depth[8];
+    uint32_t color[8];
+    unsigned active_mask;
+} trapezoid_batch;
+
+/* rasterize_batch_scalar span_walker.rs:213-283 */
+static void span_walker_batch(trapezoid_batch *b, int32_t width, int32_t height, uint32_t *cbuf, float *dbuf) {
+    if (b->count == 0) return;
+    float min_y = INFINITY, max_y = -INFINITY;
+    for (int i = 0; i < b->count; ++i) {
+        min_y = rmin(min_y, b->start_y[i]);
+        max_y = rmax(max_y, b->end_y[i]);
+    }
+    int32_t current_y = f2i(floorf(min_y));
+    const int32_t end_y = f2i(ceilf(max_y));
+    while (current_y < end_y) {
+        if (current_y >= height) break;
+        if (current_y >= 0) {
+            const float yc = (float)current_y + 0.5f; /* update_active_mask :76-84 */
+            unsigned mask = 0;
+            for (int i = 0; i < b->count; ++i)
+                if (yc >= b->start_y[i] && yc < b->end_y[i]) mask |= 1u << i;
+            b->active_mask = mask;
+            if (mask) {
+                for (int i = 0; i < b->count; ++i) {
+                    if (!(mask & (1u << i))) continue;
+                    int32_t xs = f2i(roundf(b->left_x[i])), xe = f2i(roundf(b->right_x[i]));
+                    vxo_fill_span(width, current_y, xs, xe, b->depth[i], b->color[i], cbuf, dbuf);
+                }
+            }
+        }
+        for (int i = 0; i < b->count; ++i) {
+            b->left_x[i] += b->left_slope[i];
+            b->right_x[i] += b->right_slope[i];
+        }
+        current_y += 1;
+    }
+}
+
+/* SpanWalkerRasterizer::rasterize_projected_packet span_walker.rs:116-194: one ProjectedPacket of `count` quads
+ * (NDC boxes, differential_projection.rs:295-304) into a width x height framebuffer. */
+void vxo_span_walk_packet(const float *x_min, const float *y_min, const float *x_max, const float *y_max,
+                          const float *depth_near, const uint8_t *block_type, uint32_t visibility_mask, int32_t count,
+                          int32_t width, int32_t height, uint32_t *cbuf, float *dbuf) {
+    const float vp_w = (float)width, vp_h = (float)height;
+    const float EPSILON = 0.001f;
+    trapezoid_batch cur;
+    memset(&cur, 0, sizeof(cur));
+    for (int32_t i = 0; i < count && i < 32; ++i) {
+        if (!(visibility_mask & (1u << i))) continue;
+        float sx_min = rmax((x_min[i] + 1.0f) * 0.5f * vp_w, 0.0f);
+        float sy_min = rmax((1.0f - y_max[i]) * 0.5f * vp_h, 0.0f);
+        float sx_max = rmin((x_max[i] + 1.0f) * 0.5f * vp_w + EPSILON, vp_w);
+        float sy_max = rmin((1.0f - y_min[i]) * 0.5f * vp_h + EPSILON, vp_h);
+        if (sx_min >= vp_w || sy_min >= vp_h || sx_max <= 0.0f || sy_max <= 0.0f) continue;
+        int k = cur.count;
+        cur.left_x[k] = sx_min; cur.right_x[k] = sx_max;
+        cur.left_slope[k] = 0.0f; cur.right_slope[k] = 0.0f;
+        cur.start_y[k] = sy_min; cur.end_y[k] = sy_max;
+        cur.depth[k] = depth_near[i];
+        cur.color[k] = vxo_span_walker_block_color(block_type[i]);
+        cur.active_mask |= 1u << k;
+        cur.count++;
+        if (cur.count == 8) {
+            span_walker_batch(&cur, width, height, cbuf, dbuf);
+            memset(&cur, 0, sizeof(cur));
+        }
+    }
+    if (cur.count > 0) span_walker_batch(&cur, width, height, cbuf, dbuf);
+}
+
+/* MacroTileBins::add_mesh macrotile.rs:179-224 for one screen box: returns 1 when the mesh is binned into the tile
+ * range tiles[4] = (tx0, ty0, tx1, ty1) (inclusive), 2 for a large primitive (> 25 % of the screen, not binned),
+ * 0 off-screen. */
+int vxo_macrotile_bin(int32_t min_x_in, int32_t min_y_in, int32_t max_x_in, int32_t max_y_in, int32_t fb_w, int32_t fb_h,
+                      int32_t tiles[4]) {
+    const int64_t min_x = imax(min_x_in, 0), min_y = imax(min_y_in, 0);
+    const int64_t max_x = imin(max_x_in, fb_w - 1), max_y = imin(max_y_in, fb_h - 1);
+    if (min_x > max_x || min_y > max_y) return 0;
+    const int64_t coverage = (max_x - min_x + 1) * (max_y - min_y + 1);
+    const int64_t total = (int64_t)fb_w * (int64_t)fb_h;
+    const float fraction = (float)coverage / (float)total;
+    if (fraction > 0.25f) return 2; /* LARGE_PRIMITIVE_SCREEN_FRACTION :26 */
+    const int tiles_x = (fb_w + 127) / 128, tiles_y = (fb_h + 127) / 128;
+    tiles[0] = (int32_t)(min_x / 128);
+    tiles[1] = (int32_t)(min_y / 128);
+    tiles[2] = imin((int32_t)(max_x / 128), tiles_x - 1);
+    tiles[3] = imin((int32_t)(max_y / 128), tiles_y - 1);
+    return 1;
+}
+
+/* project_mesh_aabb macrotile_renderer.rs:175-250 (the same arithmetic as main.rs:405-470) */
+static int project_mesh_aabb(const int32_t pos[3], const float vp[16], float width, float height, int32_t rect[4]) {
+    float mn[3], mx[3];
+    for (int k = 0; k < 3; ++k) {
+        float chunk_pos = (float)pos[k] * (float)CS;
+        float half = (float)CS * 0.5f;
+        float center = chunk_pos + half;
+        mn[k] = center - half;
+        mx[k] = center + half;
+    }
+    int rect_min_x = INT32_MAX, rect_min_y = INT32_MAX, rect_max_x = INT32_MIN, rect_max_y = INT32_MIN;
+    float nd = INFINITY;
+    int any_behind = 0;
+    for (int c = 0; c < 8; ++c) {
+        float cx = (c & 1) ? mx[0] : mn[0], cy = (c & 2) ? mx[1] : mn[1], cz = (c & 4) ? mx[2] : mn[2];
+        float clip[4];
+        mat4_mul_vec4(vp, cx, cy, cz, 1.0f, clip);
+        if (clip[3] <= 0.001f) any_behind = 1;
+        if (clip[3] > 0.001f) {
+            float nx = clip[0] / clip[3], ny = clip[1] / clip[3], nz = clip[2] / clip[3];
+            nd = rmin(nd, nz);
+            float sx = (nx + 1.0f) * 0.5f * width;
+            float sy = (1.0f - ny) * 0.5f * height;
+            rect_min_x = imin(rect_min_x, f2i(floorf(sx)));
+            rect_max_x = imax(rect_max_x, f2i(ceilf(sx)));
+            rect_min_y = imin(rect_min_y, f2i(floorf(sy)));
+            rect_max_y = imax(rect_max_y, f2i(ceilf(sy)));
+        }
+    }
+    if (any_behind) {
+        rect_min_x = 0; rect_min_y = 0; rect_max_x = f2i(width) - 1; rect_max_y = f2i(height) - 1;
+    } else {
+        if (isinf(nd) || nd > 1.0f) return 0;
+        rect_min_x = imax(rect_min_x, 0); rect_min_y = imax(rect_min_y, 0);
+        rect_max_x = imin(rect_max_x, f2i(width) - 1); rect_max_y = imin(rect_max_y, f2i(height) - 1);
+        if (rect_min_x > rect_max_x || rect_min_y > rect_max_y) return 0;
+    }
+    rect[0] = rect_min_x; rect[1] = rect_min_y; rect[2] = rect_max_x; rect[3] = rect_max_y;
+    return 1;
+}
+
+/* render_frame_macrotile macrotile_renderer.rs:51-170: clear, project every mesh's chunk box, bin into 128x128
+ * macrotiles (meshes covering > 25 % of the screen go to the large-primitive list), per tile render the binned meshes
+ * in list order and then the large primitives through render_mesh_tiny_quads with the tile as PixelTarget, flush the
+ * tile colours.  The Hi-Z buffer argument of the reference is only cleared there, never consulted.  Rayon's tile
+ * parallelism cannot change the result (tiles are disjoint).
+ *   color       W*H, the framebuffer colour the reference flushes
+ *   tile_depth  W*H or NULL: the tiles' depth buffers (the reference drops them; the framebuffer's own depth buffer
+ *               stays at +inf) -- a diagnostic for the tests
+ *   projected_out  mesh ids that survived project_mesh_aabb, list order;  returns their number (the reference's
+ *               return value)
+ *   kind_out    per projected mesh: 1 binned, 2 large primitive (drawn after the binned ones in every tile) */
+int vxo_render_frame_macrotile(const vxo_mesh_batch *mb, const int32_t *mesh_ids, int32_t n_meshes, const float vp[16],
+                               const vxo_frame_config *cfg, const vxo_atlas *atlas, uint32_t *color, float *tile_depth,
+                               int32_t *projected_out, int32_t *kind_out) {
+    const int W = cfg->width, H = cfg->height;
+    const size_t npx = (size_t)W * (size_t)H;
+    float *depth = tile_depth ? tile_depth : (float *)malloc(sizeof(float) * npx);
+    for (size_t i = 0; i < npx; ++i) { color[i] = cfg->clear_color; depth[i] = INFINITY; }
+    int32_t n_proj = 0;
+    int32_t *proj = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_meshes > 0 ? n_meshes : 1));
+    int32_t *kind = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_meshes > 0 ? n_meshes : 1));
+    int32_t *tiles = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)(n_meshes > 0 ? n_meshes : 1));
+    int n_large = 0;
+    for (int32_t i = 0; i < n_meshes; ++i) {
+        int32_t rect[4];
+        if (!project_mesh_aabb(mb->positions + 3 * (size_t)mesh_ids[i], vp, (float)W, (float)H, rect)) continue;
+        proj[n_proj] = mesh_ids[i];
+        kind[n_proj] = vxo_macrotile_bin(rect[0], rect[1], rect[2], rect[3], W, H, tiles + 4 * (size_t)n_proj);
+        if (kind[n_proj] == 2) n_large++;
+        if (projected_out) projected_out[n_proj] = mesh_ids[i];
+        if (kind_out) kind_out[n_proj] = kind[n_proj];
+        n_proj++;
+    }
+    if (n_proj > 0) {
+        const int tiles_x = (W + 127) / 128, tiles_y = (H + 127) / 128;
+        for (int ty = 0; ty < tiles_y; ++ty)
+            for (int tx = 0; tx < tiles_x; ++tx) {
+                const int x0 = tx * 128, y0 = ty * 128;
+                target_t tg = {W, H, x0, y0, imin(x0 + 128, W) - x0, imin(y0 + 128, H) - y0, color, depth, cfg, atlas};
+                for (int32_t j = 0; j < n_proj; ++j) /* bins.get_bin(tx, ty), push order = list order */
+                    if (kind[j] == 1 && tx >= tiles[4 * j] && tx <= tiles[4 * j + 2] && ty >= tiles[4 * j + 1] && ty <= tiles[4 * j + 3])
+                        render_mesh_tiny_quads(mb, proj[j], vp, &tg);
+                if (n_large)
+                    for (int32_t j = 0; j < n_proj; ++j)
+                        if (kind[j] == 2) render_mesh_tiny_quads(mb, proj[j], vp, &tg);
+            }
+    }
+    free(proj); free(kind); free(tiles);
+    if (!tile_depth) free(depth);
+    return n_proj;
+}

@@ -146,6 +146,28 @@ void vxo_transform_vertices(const uint8_t *verts, int32_t n, const float offset[
 void vxo_quad_clip_vertices(int face, uint8_t slice_pos, uint8_t u, uint8_t v, uint8_t w, uint8_t h,
                             const int32_t chunk_pos[3], const float vp[16], float clip[16]);
 
+
+/* ---- adjacent rasterizers -------------------------- */
+
+/* SpanWalkerRasterizer::get_block_color span_walker.rs:386-396 */
+uint32_t vxo_span_walker_block_color(uint8_t block_type);
+/* FrameSlice::fill_span span_walker.rs:412-441: pixels [x_start, x_end) of row y, depth test `<`. */
+void vxo_fill_span(int32_t width, int32_t y, int32_t x_start, int32_t x_end, float depth, uint32_t color,
+                   uint32_t *cbuf, float *dbuf);
+/* SpanWalkerRasterizer::rasterize_projected_packet span_walker.rs:116-283 (scalar batch path) for one
+ * ProjectedPacket (count <= 32 NDC boxes + constant depth + block type, visibility bit per quad). */
+void vxo_span_walk_packet(const float *x_min, const float *y_min, const float *x_max, const float *y_max,
+                          const float *depth_near, const uint8_t *block_type, uint32_t visibility_mask, int32_t count,
+                          int32_t width, int32_t height, uint32_t *cbuf, float *dbuf);
+/* MacroTileBins::add_mesh macrotile.rs:179-224: 1 binned (tiles = tx0,ty0,tx1,ty1 inclusive), 2 large primitive,
+ * 0 off-screen. */
+int vxo_macrotile_bin(int32_t min_x, int32_t min_y, int32_t max_x, int32_t max_y, int32_t fb_w, int32_t fb_h,
+                      int32_t tiles[4]);
+/* render_frame_macrotile macrotile_renderer.rs:51-170 (see vx_oracle.c). */
+int vxo_render_frame_macrotile(const vxo_mesh_batch *mb, const int32_t *mesh_ids, int32_t n_meshes, const float vp[16],
+                               const vxo_frame_config *cfg, const vxo_atlas *atlas, uint32_t *color, float *tile_depth,
+                               int32_t *projected_out, int32_t *kind_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -499,3 +499,42 @@ def test_orthographic_subpixel_quads(ctx, ob):
             drawn += int((oc != 0xFF87CEEB).sum())
     assert drawn > 500
     batch.release()
+
+
+# ---- render_frame_macrotile (macrotile_renderer.rs:51-170) --------------------------------------
+@pytest.mark.parametrize("w,h,cam_i", [(640, 360, 0), (640, 360, 3), (1280, 720, 1), (500, 300, 5), (1920, 1080, 2)])
+def test_macrotile_frame_bit_exact(ctx, ob, scene5, w, h, cam_i):
+    """Colour, the tiles' depth buffers and the draw order (list order, large primitives last) of the macrotile
+    renderer, bit for bit; the mesh list is the caller's (no filter A, no near-depth sort)."""
+    _, p, batch, ref = scene5
+    cam = vx_scenes.path_camera(cam_i, w, h)
+    vp = cam.view_projection()
+    ids = np.flatnonzero(ref.has_mesh != 0).astype(np.int32)
+    ids = ids[np.random.default_rng(cam_i).permutation(ids.size)]  # list order is the caller's, not chunk order
+    ocfg = ob.default_frame_config(w, h)
+    oc, od, oproj, okind = ob.render_frame_macrotile(ref, ids, vp, ocfg, ob.default_atlas(), want_kinds=True)
+    cfg = api.default_frame_config(w, h)
+    color, depth, proj = api.render_frame_macrotile(batch, ids, vp, cfg, ctx=ctx)
+    assert proj.tolist() == oproj[okind == 1].tolist() + oproj[okind == 2].tolist()
+    assert np.array_equal(depth.view(np.uint32), od.view(np.uint32)), "tile depth not bit-identical"
+    assert np.array_equal(color, oc), "colour not bit-identical"
+    assert int((color != cfg.clear_color).sum()) > 0
+    # the stripe renderer covers the same pixels; it only differs where a depth test flips
+    c2, d2, _ = api.render_frame(batch, vp, cam.position, cfg, mesh_ids=ids, ctx=ctx)
+    assert np.array_equal(c2 != cfg.clear_color, color != cfg.clear_color)
+    # and the flag alone (vx_render_frame with cfg.macrotile = 1) is the same renderer
+    cfg.macrotile = 1
+    c3, d3, s3 = api.render_frame(batch, vp, cam.position, cfg, mesh_ids=ids, ctx=ctx)
+    assert np.array_equal(c3, oc) and np.array_equal(d3.view(np.uint32), od.view(np.uint32)) and s3.tolist() == proj.tolist()
+
+
+def test_macrotile_frame_empty_list_and_colour_only(ctx, ob, scene5):
+    _, p, batch, ref = scene5
+    cfg = api.default_frame_config(320, 200)
+    cam = vx_scenes.path_camera(0, 320, 200)
+    color, depth, proj = api.render_frame_macrotile(batch, np.zeros(0, dtype=np.int32), cam.view_projection(), cfg, ctx=ctx)
+    assert proj.size == 0 and (color == cfg.clear_color).all() and np.isinf(depth).all()
+    ids = np.flatnonzero(ref.has_mesh != 0).astype(np.int32)
+    oc = ob.render_frame_macrotile(ref, ids, cam.view_projection(), ob.default_frame_config(320, 200), ob.default_atlas())[0]
+    color, depth, proj = api.render_frame_macrotile(batch, ids, cam.view_projection(), cfg, want_tile_depth=False, ctx=ctx)
+    assert depth is None and np.array_equal(color, oc)

@@ -375,3 +375,176 @@ def test_face_basis_backface_sign_and_slices(ob):
     b0, b15, b31 = (ob.face_basis(2, (0, 0, 0), s, ident) for s in (0, 15, 31))
     assert abs(b0[0][1] - 0.0) < 1e-3 and abs(b15[0][1] - 15.0) < 1e-3 and abs(b31[0][1] - 31.0) < 1e-3
     assert np.array_equal(b0[1], b15[1]) and np.array_equal(b0[2], b31[2])
+
+
+# ---- span walker KATs: src/rendering/span_walker.rs:615-678, tests/span_walker_{differential_tests,bug_reproduction}.rs -----
+def _blank(w, h):
+    return np.zeros((h, w), dtype=np.uint32), np.full((h, w), np.inf, dtype=np.float32)  # Framebuffer::new
+
+
+def test_fill_span_basic_and_depth_test(ob):  # span_walker.rs:615-656
+    c, d = _blank(64, 64)
+    ob.fill_span(c, d, 32, 10, 50, 0.5, 0xFF0000FF)
+    assert (c[32, 10:50] == 0xFF0000FF).all() and (d[32, 10:50] == np.float32(0.5)).all()
+    assert c[32, 9] == 0 and c[32, 50] == 0 and int((c != 0).sum()) == 40
+    ob.fill_span(c, d, 32, 10, 50, 0.7, 0x00FF00FF)  # farther: rejected
+    assert c[32, 25] == 0xFF0000FF and d[32, 25] == np.float32(0.5)
+    ob.fill_span(c, d, 32, 10, 50, 0.3, 0x0000FFFF)  # nearer: wins
+    assert c[32, 25] == 0x0000FFFF and d[32, 25] == np.float32(0.3)
+    ob.fill_span(c, d, 32, 10, 50, 0.3, 0x12345678)  # equal depth: `<` keeps the first
+    assert c[32, 25] == 0x0000FFFF
+    # clamps (:422-428): x_start into [0, W-1], x_end into [0, W]; empty after the clamp -> nothing
+    c, d = _blank(64, 4)
+    ob.fill_span(c, d, 1, -20, 5, 0.5, 7)
+    ob.fill_span(c, d, 2, 60, 500, 0.5, 7)
+    ob.fill_span(c, d, 3, 70, 90, 0.5, 7)   # x_start clamps to 63, x_end to 64: the last pixel IS written
+    ob.fill_span(c, d, 0, 30, 30, 0.5, 7)
+    assert (c[1] == 7).sum() == 5 and (c[2] == 7).sum() == 4 and (c[3] == 7).sum() == 1 and c[3, 63] == 7 and (c[0] == 7).sum() == 0
+
+
+def test_fill_span_partial_occlusion(ob):  # span_walker.rs:876-906
+    c, d = _blank(128, 128)
+    d[64, 0::2] = 0.3; c[64, 0::2] = 0xAAAAAA00
+    d[64, 1::2] = 0.7; c[64, 1::2] = 0xBBBBBB00
+    ob.fill_span(c, d, 64, 0, 128, 0.5, 0xFF00FF00)
+    assert (c[64, 0::2] == 0xAAAAAA00).all() and (d[64, 0::2] == np.float32(0.3)).all()
+    assert (c[64, 1::2] == 0xFF00FF00).all() and (d[64, 1::2] == np.float32(0.5)).all()
+
+
+def test_span_walker_simple_quad(ob):  # span_walker.rs:658-681
+    c, d = _blank(128, 128)
+    ob.span_walk_quads(c, d, [-0.5], [-0.5], [0.5], [0.5], [0.5], [1])
+    assert c[64, 64] == 0x00FF00FF and d[64, 64] == np.float32(0.5)
+    assert int((c != 0).sum()) == 64 * 64 and (c[32:96, 32:96] != 0).all()
+
+
+def test_span_walker_block_colours(ob):  # span_walker.rs:386-396
+    assert [ob.span_walker_block_color(b) for b in (0, 1, 2, 3, 4, 255)] == [0, 0x00FF00FF, 0x8B4513FF, 0x808080FF, 0, 0]
+
+
+def test_span_walker_single_quad_fills_about_100_px(ob):  # tests/span_walker_differential_tests.rs:11-56
+    c, d = _blank(100, 100)
+    ob.span_walk_quads(c, d, [-0.6], [-0.2], [-0.4], [0.0], [0.5], [1])
+    assert 80 <= int((c != 0).sum()) <= 120
+
+
+def test_span_walker_depth_testing_across_packets(ob):  # tests/span_walker_differential_tests.rs:58-112
+    c, d = _blank(100, 100)
+    ob.span_walk_quads(c, d, [-0.5], [-0.5], [0.5], [0.5], [0.7], [1])
+    ob.span_walk_quads(c, d, [-0.3], [-0.3], [0.3], [0.3], [0.3], [2])
+    assert abs(float(d[50, 50]) - 0.3) < 0.1 and c[50, 50] == 0x8B4513FF
+    assert c[30, 30] == 0x00FF00FF and d[30, 30] == np.float32(0.7)
+
+
+def test_span_walker_visibility_mask_and_two_quads(ob):  # tests/span_walker_differential_tests.rs:114-160 (+ mask)
+    c, d = _blank(200, 200)
+    ob.span_walk_quads(c, d, [-0.8, 0.2], [-0.4, -0.4], [-0.2, 0.8], [0.4, 0.4], [0.5, 0.5], [1, 2])
+    assert int((c == 0x00FF00FF).sum()) > 0 and int((c == 0x8B4513FF).sum()) > 0
+    c2, d2 = _blank(200, 200)
+    ob.span_walk_quads(c2, d2, [-0.8, 0.2], [-0.4, -0.4], [-0.2, 0.8], [0.4, 0.4], [0.5, 0.5], [1, 2], visible=[0, 1])
+    assert int((c2 == 0x00FF00FF).sum()) == 0 and np.array_equal(c2 == 0x8B4513FF, c == 0x8B4513FF)
+
+
+def test_span_walker_fractional_start_and_vertical_gaps(ob):  # tests/span_walker_bug_reproduction.rs:10-140
+    c, d = _blank(200, 200)
+    ob.span_walk_quads(c, d, [-0.5], [-0.892], [0.5], [-0.85], [0.5], [1])
+    assert int((c != 0).sum()) > 0
+    c, d = _blank(200, 200)
+    ob.span_walk_quads(c, d, [-0.5, -0.5], [-0.9, -0.8], [0.5, 0.5], [-0.85, -0.75], [0.5, 0.5], [1, 2])
+    assert int((c != 0).sum()) >= 500 and int((c == 0x00FF00FF).sum()) > 0 and int((c == 0x8B4513FF).sum()) > 0
+    c, d = _blank(200, 200)
+    k = np.arange(3, dtype=np.float32) * np.float32(0.15)
+    ob.span_walk_quads(c, d, [-0.4] * 3, np.float32(-0.9) + k, [0.4] * 3, np.float32(-0.87) + k, [0.5] * 3, [1, 2, 3])
+    assert int((c != 0).sum()) >= 100
+
+
+def test_span_walker_rows_are_sampled_at_pixel_centres(ob):  # span_walker.rs:237-247 (y + 0.5 in [start_y, end_y))
+    # 200 px tall: NDC y in [0.795, 0.9] -> screen rows [10.0, 20.5(+eps)): rows 10 .. 20 (row 20's centre 20.5 < 20.501)
+    c, d = _blank(200, 200)
+    ob.span_walk_quads(c, d, [-0.5], [0.795], [0.5], [0.9], [0.5], [3])
+    rows = np.flatnonzero((c != 0).any(axis=1))
+    ymin = (np.float32(1.0) - np.float32(0.9)) * np.float32(0.5) * np.float32(200.0)
+    ymax = (np.float32(1.0) - np.float32(0.795)) * np.float32(0.5) * np.float32(200.0) + np.float32(0.001)
+    want = [y for y in range(200) if np.float32(y + 0.5) >= ymin and np.float32(y + 0.5) < ymax]
+    assert list(rows) == want and len(want) in (10, 11)
+    cols = np.flatnonzero((c != 0).any(axis=0))  # columns: round() of the screen box, [50, 150)
+    assert cols[0] == 50 and cols[-1] == 149
+
+
+def test_span_walker_more_than_eight_quads_batches(ob):  # span_walker.rs:181-192: batches of 8 do not change the result
+    rng = np.random.default_rng(5)
+    n = 70
+    x0 = rng.uniform(-1.2, 1.0, n).astype(np.float32); x1 = x0 + rng.uniform(0.0, 0.6, n).astype(np.float32)
+    y0 = rng.uniform(-1.2, 1.0, n).astype(np.float32); y1 = y0 + rng.uniform(0.0, 0.6, n).astype(np.float32)
+    z = rng.choice(np.linspace(0.1, 0.9, 7).astype(np.float32), n)
+    bt = rng.integers(0, 4, n).astype(np.uint8)
+    c, d = _blank(160, 120)
+    ob.span_walk_quads(c, d, x0, y0, x1, y1, z, bt)
+    # serial restatement of the definition: quads in order, rows by pixel centre, columns by round(), depth test `<`
+    c2, d2 = _blank(160, 120)
+    W, H = np.float32(160), np.float32(120)
+    for i in range(n):
+        sx0 = max((x0[i] + np.float32(1)) * np.float32(0.5) * W, np.float32(0)); sy0 = max((np.float32(1) - y1[i]) * np.float32(0.5) * H, np.float32(0))
+        sx1 = min((x1[i] + np.float32(1)) * np.float32(0.5) * W + np.float32(0.001), W); sy1 = min((np.float32(1) - y0[i]) * np.float32(0.5) * H + np.float32(0.001), H)
+        if sx0 >= W or sy0 >= H or sx1 <= 0 or sy1 <= 0:
+            continue
+        xs = int(np.floor(sx0 + np.float32(0.5))); xe = int(np.floor(sx1 + np.float32(0.5)))  # round(), positive values
+        xs = min(max(xs, 0), 159); xe = min(max(xe, 0), 160)
+        for y in range(120):
+            if np.float32(y + 0.5) >= sy0 and np.float32(y + 0.5) < sy1 and xs < xe:
+                m = z[i] < d2[y, xs:xe]
+                d2[y, xs:xe][m] = z[i]
+                c2[y, xs:xe][m] = ob.span_walker_block_color(int(bt[i]))
+    assert np.array_equal(c, c2) and np.array_equal(d.view(np.uint32), d2.view(np.uint32))
+
+
+# ---- macrotile KATs: src/rendering/macrotile.rs:393-440 ----------------------------------------------------------
+def test_macrotile_binning(ob):
+    assert ob.macrotile_bin(0, 0, 100, 100, 1280, 720) == (1, (0, 0, 0, 0))          # :404-418 tile (0,0) only
+    assert ob.macrotile_bin(64, 64, 192, 192, 1280, 720) == (1, (0, 0, 1, 1))        # :420-433 four tiles
+    assert ob.macrotile_bin(0, 0, 1279, 719, 1280, 720)[0] == 2                       # :435-445 large primitive
+    assert ob.macrotile_bin(150, 0, 250, 100, 1280, 720) == (1, (1, 0, 1, 0))        # :447-465 second mesh -> tile (1,0)
+    assert ob.macrotile_bin(-50, -50, -1, -1, 1280, 720)[0] == 0                     # off-screen :197-199
+    assert ob.macrotile_bin(0, 0, 639, 359, 1280, 720)[0] == 1                       # exactly 25 %: not "more than"
+    assert ob.macrotile_bin(0, 0, 640, 359, 1280, 720)[0] == 2
+    assert ob.macrotile_bin(1200, 700, 5000, 5000, 1280, 720) == (1, (9, 5, 9, 5))   # clamped to the last tile
+
+
+def test_macrotile_frame_covers_the_same_pixels_as_the_stripe_frame(ob):
+    """render_frame_macrotile (macrotile_renderer.rs:51-170) draws the same meshes through the same span rasterizer,
+    tile by tile: the covered pixel set equals the stripe renderer's (main.rs), colours differ only where the per-tile
+    restart of the span interpolation or the draw order (list order, no near-depth sort) flips a depth test."""
+    import vx_scenes
+    pos, world, p, v, nb = vx_scenes.terrain_scene(3)
+    mb = ob.mesh_chunks(v, nb, None, p)
+    w, h = 400, 300
+    cam = vx_scenes.main_camera(w, h)
+    vp = cam.view_projection()
+    vis = ob.cull_chunks(p, vp, cam.position, 3)
+    ids = np.flatnonzero((vis != 0) & (mb.has_mesh != 0)).astype(np.int32)
+    cfg = ob.default_frame_config(w, h, n_threads=2)
+    atlas = ob.default_atlas()
+    c_s, d_s, surv = ob.render_frame(mb, ids, vp, cam.position, cfg, atlas)
+    c_m, d_m, proj = ob.render_frame_macrotile(mb, ids, vp, cfg, atlas)
+    assert sorted(proj.tolist()) == sorted(surv.tolist()) and proj.tolist() == [i for i in ids.tolist() if i in set(surv.tolist())]
+    assert np.array_equal(c_m != cfg.clear_color, c_s != cfg.clear_color)
+    assert np.array_equal(np.isfinite(d_m), np.isfinite(d_s))
+    assert float((c_m != c_s).mean()) < 0.01 and float(np.abs(d_m[np.isfinite(d_m)] - d_s[np.isfinite(d_s)]).max()) < 1e-3
+    # one tile (a 100 x 90 frame) is exactly the full-frame target of render_mesh, meshes drawn in list order
+    cfg1 = ob.default_frame_config(100, 90)
+    cam1 = vx_scenes.main_camera(100, 90)
+    vp1 = cam1.view_projection()
+    c1, d1, proj1 = ob.render_frame_macrotile(mb, ids, vp1, cfg1, atlas)
+    c2 = np.full((90, 100), cfg1.clear_color, dtype=np.uint32); d2 = np.full((90, 100), np.inf, dtype=np.float32)
+    for i in proj1:
+        ob.render_mesh(mb, int(i), vp1, cfg1, atlas, (0, 0, 100, 90), c2, d2)
+    assert proj1.size > 0
+    kinds1 = ob.render_frame_macrotile(mb, ids, vp1, cfg1, atlas, want_kinds=True)[3]
+    if not (kinds1 == 2).any():  # large primitives are drawn last, so the order differs when there are any
+        assert np.array_equal(c1, c2) and np.array_equal(d1.view(np.uint32), d2.view(np.uint32))
+    else:
+        assert np.array_equal(c1 != cfg1.clear_color, c2 != cfg1.clear_color)
+        c3 = np.full((90, 100), cfg1.clear_color, dtype=np.uint32); d3 = np.full((90, 100), np.inf, dtype=np.float32)
+        for i in list(proj1[kinds1 == 1]) + list(proj1[kinds1 == 2]):
+            ob.render_mesh(mb, int(i), vp1, cfg1, atlas, (0, 0, 100, 90), c3, d3)
+        assert np.array_equal(c1, c3) and np.array_equal(d1.view(np.uint32), d3.view(np.uint32))
