@@ -462,6 +462,23 @@ class Rasterizer:
         """rasterizer.rs:423: FrameTile rectangle."""
         self._render(batch, mesh_id, view_proj, framebuffer, (x0, y0, tw, th))
 
+    def render_mesh_with_up(self, batch: MeshBatch, mesh_id: int, view_proj, framebuffer: Framebuffer, camera_up):
+        """rasterizer.rs:399: whole framebuffer; span renderer iff the camera is level (|up.y| >= 0.995), else barycentric."""
+        vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+        up = np.ascontiguousarray(camera_up, dtype=np.float32).reshape(3)
+        cfg = self._cfg(framebuffer.width, framebuffer.height)
+        self.ctx.check(self.ctx.lib.vx_render_mesh_with_up(self.ctx.handle, batch.handle, int(mesh_id), _p(vp), C.byref(cfg), _p(up),
+                                                           _p(framebuffer.color_buffer), _p(framebuffer.depth_buffer)))
+
+    def render_mesh_tiny_quads(self, batch: MeshBatch, mesh_id: int, view_proj, framebuffer: Framebuffer, rect, use_span_renderer: bool):
+        """rasterizer.rs:782: target = rect (x0, y0, w, h) of the framebuffer; use_span_renderer False = barycentric path."""
+        vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+        rect = np.ascontiguousarray(rect, dtype=np.int32).reshape(4)
+        cfg = self._cfg(framebuffer.width, framebuffer.height)
+        self.ctx.check(self.ctx.lib.vx_render_mesh_tiny_quads(self.ctx.handle, batch.handle, int(mesh_id), _p(vp), C.byref(cfg), _p(rect),
+                                                              1 if use_span_renderer else 0, _p(framebuffer.color_buffer),
+                                                              _p(framebuffer.depth_buffer)))
+
 
 def render_frame(batch: MeshBatch, view_proj, camera_position, cfg: VxFrameConfig, mesh_ids=None, view_distance: int = 0,
                  color_out=None, depth_out=None, want_depth: bool = True, ctx: Optional[Context] = None, survivors_out=None):

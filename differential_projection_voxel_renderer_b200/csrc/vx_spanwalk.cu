@@ -11,12 +11,12 @@
 // `depth < stored` loses it.  Four launches: setup (screen boxes + work count per quad), scan, fill, resolve.
 #include "vx_common.cuh"
 #include "vx_math.cuh"
+#include "vx_scan.cuh"
 
 namespace {
 
 constexpr int SW_THREADS = 256;
 constexpr int SW_ROWS = 8;         // rows of one fill task
-constexpr int SW_SCAN_THREADS = 1024;
 
 struct SpanRec {
     int32_t y0, y1;  // rows y0 .. y1 inclusive (y0 > y1: nothing)
@@ -89,31 +89,6 @@ __global__ void __launch_bounds__(SW_THREADS) spanwalk_setup_kernel(int mode, co
     n_tasks[i] = r.y0 <= r.y1 ? (uint32_t)((r.y1 - r.y0) / SW_ROWS + 1) : 0u;
 }
 
-// exclusive prefix sum of n_tasks (one CTA; n is the number of quads of one call, not a per-frame hot loop)
-__global__ void __launch_bounds__(SW_SCAN_THREADS) spanwalk_scan_kernel(const uint32_t *__restrict__ n_tasks, int n, unsigned long long *__restrict__ task_base,
-                                                                       SpanCtl *ctl) {
-    __shared__ unsigned long long part[SW_SCAN_THREADS];
-    const int tid = threadIdx.x;
-    const int per = (n + SW_SCAN_THREADS - 1) / SW_SCAN_THREADS;
-    const int lo = min(tid * per, n), hi = min(lo + per, n);
-    unsigned long long s = 0;
-    for (int i = lo; i < hi; ++i) s += n_tasks[i];
-    part[tid] = s;
-    __syncthreads();
-    for (int o = 1; o < SW_SCAN_THREADS; o <<= 1) { // Hillis-Steele inclusive scan
-        unsigned long long v = tid >= o ? part[tid - o] : 0ull;
-        __syncthreads();
-        part[tid] += v;
-        __syncthreads();
-    }
-    unsigned long long run = part[tid] - s;
-    for (int i = lo; i < hi; ++i) {
-        task_base[i] = run;
-        run += n_tasks[i];
-    }
-    if (tid == SW_SCAN_THREADS - 1) ctl->total_tasks = part[tid];
-}
-
 __global__ void __launch_bounds__(SW_THREADS) spanwalk_init_keys_kernel(const float *__restrict__ depth, size_t npx, unsigned long long *__restrict__ keys) {
     for (size_t p = (size_t)blockIdx.x * SW_THREADS + threadIdx.x; p < npx; p += (size_t)gridDim.x * SW_THREADS) {
         const float d = depth[p];
@@ -129,14 +104,7 @@ __global__ void __launch_bounds__(SW_THREADS) spanwalk_fill_kernel(const SpanRec
     const int lane = threadIdx.x & 31;
     const unsigned long long n_warps = (unsigned long long)gridDim.x * (SW_THREADS / 32);
     for (unsigned long long t = (unsigned long long)blockIdx.x * (SW_THREADS / 32) + (threadIdx.x >> 5); t < total; t += n_warps) {
-        // owner of task t = the right-most record with task_base <= t: a record without tasks has the base of its
-        // successor, so it is never right-most among those <= t unless every later base is > t, and then its own is too
-        int lo = 0, hi = n - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (task_base[mid] <= t) lo = mid;
-            else hi = mid - 1;
-        }
+        const int lo = vx_task_owner(task_base, n, t);
         const SpanRec r = recs[lo];
         const int chunk = (int)(t - task_base[lo]);
         const int ya = r.y0 + chunk * SW_ROWS, yb = min(ya + SW_ROWS - 1, r.y1);
@@ -184,7 +152,7 @@ int span_walk_device(VxContext *ctx, int mode, const float *d_f, const uint8_t *
     VX_CHECK_LAUNCH(ctx);
     spanwalk_setup_kernel<<<(n + SW_THREADS - 1) / SW_THREADS, SW_THREADS, 0, ctx->stream>>>(mode, d_f, d_b, d_i, d_u, n, W, H, recs, cnt);
     VX_CHECK_LAUNCH(ctx);
-    spanwalk_scan_kernel<<<1, SW_SCAN_THREADS, 0, ctx->stream>>>(cnt, n, tb, ctl);
+    vx_scan_counts_kernel<<<1, VX_SCAN_THREADS, 0, ctx->stream>>>(cnt, n, tb, &ctl->total_tasks);
     VX_CHECK_LAUNCH(ctx);
     spanwalk_fill_kernel<<<ctx->num_sms * 8, SW_THREADS, 0, ctx->stream>>>(recs, tb, n, ctl, W, keys);
     VX_CHECK_LAUNCH(ctx);

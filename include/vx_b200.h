@@ -323,6 +323,21 @@ VX_API int vx_fill_spans(VxContext *ctx, const int32_t *y, const int32_t *x_star
 VX_API int vx_render_mesh(VxContext *ctx, const VxMeshBatch *batch, int32_t mesh_id, const float vp[16],
                    const VxFrameConfig *cfg, const int32_t rect[4], uint32_t *color_inout, float *depth_inout);
 
+/* Rasterizer::render_mesh_tiny_quads(mesh, view_proj, target, use_span_renderer) (rasterizer.rs:782-929), the pub
+ * generic both mesh paths go through.  use_span_renderer != 0: vx_render_mesh.  0: the barycentric rasterizer
+ * render_tiny_quad / render_triangle_from_clip_textured (:932-1071, :1881-2107): box of the clipped triangle
+ * intersected with the framebuffer and rect, `area < 0.1` triangles dropped, edge functions advanced by one rounded
+ * add per pixel and per row from the box's top-left pixel centre, coverage w0, w1, w2 >= 0, depth and perspective-
+ * correct texel from the barycentric weights.  W x H host arrays, read-modify-write; exact vertex arithmetic only
+ * (cfg->differential_projection is ignored on this path). */
+VX_API int vx_render_mesh_tiny_quads(VxContext *ctx, const VxMeshBatch *batch, int32_t mesh_id, const float vp[16],
+                              const VxFrameConfig *cfg, const int32_t rect[4], int32_t use_span_renderer,
+                              uint32_t *color_inout, float *depth_inout);
+/* Rasterizer::render_mesh_with_up (rasterizer.rs:399-411): the whole framebuffer; the span renderer when the camera
+ * is level (|camera_up.y| >= 0.995, is_camera_level :377-382), the barycentric one otherwise. */
+VX_API int vx_render_mesh_with_up(VxContext *ctx, const VxMeshBatch *batch, int32_t mesh_id, const float vp[16],
+                           const VxFrameConfig *cfg, const float camera_up[3], uint32_t *color_inout, float *depth_inout);
+
 /* ---- hyper-pipeline pieces ------------------------------------------- */
 
 /* `FacePacket32` face_packets.rs:13-25: up to 32 quads of one face direction, structure of arrays, 32-byte aligned. */

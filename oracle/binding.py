@@ -190,6 +190,21 @@ def render_mesh(mb: MeshBatch, mesh_id, vp, cfg: FrameConfig, atlas: Atlas, rect
                           _p(color), _p(depth))
 
 
+def render_mesh_tiny_quads(mb: MeshBatch, mesh_id, vp, cfg: FrameConfig, atlas: Atlas, rect, use_span_renderer, color, depth):
+    vp = np.ascontiguousarray(vp, dtype=np.float32).reshape(16)
+    rect = np.ascontiguousarray(rect, dtype=np.int32).reshape(4)
+    v = mb.view()
+    lib().vxo_render_mesh_tiny_quads(C.byref(v), C.c_int32(mesh_id), _p(vp), C.byref(cfg), C.byref(atlas), _p(rect),
+                                     C.c_int32(1 if use_span_renderer else 0), _p(color), _p(depth))
+
+
+def render_mesh_with_up(mb: MeshBatch, mesh_id, vp, cfg: FrameConfig, atlas: Atlas, camera_up, color, depth):
+    vp = np.ascontiguousarray(vp, dtype=np.float32).reshape(16)
+    up = np.ascontiguousarray(camera_up, dtype=np.float32).reshape(3)
+    v = mb.view()
+    lib().vxo_render_mesh_with_up(C.byref(v), C.c_int32(mesh_id), _p(vp), C.byref(cfg), C.byref(atlas), _p(up), _p(color), _p(depth))
+
+
 def render_frame(mb: MeshBatch, mesh_ids, vp, cam_pos, cfg: FrameConfig, atlas: Atlas):
     """Returns (color (H,W) u32, depth (H,W) f32, survivors (k,) i32 in draw order)."""
     mesh_ids = np.ascontiguousarray(mesh_ids, dtype=np.int32)

@@ -461,6 +461,7 @@ typedef struct {
     uint32_t *color; float *depth;
     const vxo_frame_config *cfg;
     const vxo_atlas *atlas;
+    int barycentric;    /* render_mesh_tiny_quads(.., use_span_renderer = false) */
 } target_t;
 
 /* rasterizer.rs:2628-2641 */
@@ -622,6 +623,90 @@ static void render_triangle_span_from_clip(const clip_vtx tri_in[3], int block_t
     }
 }
 
+/* Rasterizer::edge_function rasterizer.rs:2556-2558 */
+static inline float edge_function(float ax, float ay, float bx, float by, float cx, float cy) {
+    return (cx - ax) * (by - ay) - (cy - ay) * (bx - ax);
+}
+
+/* render_triangle_from_clip_textured rasterizer.rs:1881-2107: the barycentric rasterizer the mesh path falls back to
+ * when the camera is rolled (render_mesh_with_up with |up.y| < 0.995, :377-411) or when render_mesh_tiny_quads is
+ * called with use_span_renderer = false.  Edge functions advance by one rounded add per pixel / per row from the top-left
+ * pixel of the triangle's box clipped to the framebuffer and the target rect. */
+static void render_triangle_from_clip_textured(const clip_vtx tri_in[3], int block_type, float light, target_t *tg) {
+    const float NEAR_W_EPS = 0.001f;
+    clip_vtx tris[2][3];
+    int tri_count = clip_triangle_near_textured(tri_in, NEAR_W_EPS, tris);
+    if (tri_count == 0) return;
+    const float fb_width = (float)tg->W, fb_height = (float)tg->H;
+    const int tex_id = block_type;
+    for (int ti = 0; ti < tri_count; ++ti) {
+        const clip_vtx *tri = tris[ti];
+        const float w0c = tri[0].pos[3], w1c = tri[1].pos[3], w2c = tri[2].pos[3];
+        float ndc[3][3];
+        for (int i = 0; i < 3; ++i)
+            for (int k = 0; k < 3; ++k) ndc[i][k] = tri[i].pos[k] / tri[i].pos[3];
+        if (tg->cfg->backface_culling) {
+            float v01x = ndc[1][0] - ndc[0][0], v01y = ndc[1][1] - ndc[0][1];
+            float v02x = ndc[2][0] - ndc[0][0], v02y = ndc[2][1] - ndc[0][1];
+            float cross_z = v01x * v02y - v01y * v02x;
+            if (cross_z <= 0.0f) continue;
+        }
+        float px[3], py[3];
+        for (int i = 0; i < 3; ++i) {
+            px[i] = (ndc[i][0] + 1.0f) * 0.5f * fb_width;
+            py[i] = (1.0f - ndc[i][1]) * 0.5f * fb_height;
+        }
+        const float z0 = ndc[0][2], z1 = ndc[1][2], z2 = ndc[2][2];
+        int min_x = f2i(floorf(rmin(rmin(px[0], px[1]), px[2])));
+        int max_x = f2i(ceilf(rmax(rmax(px[0], px[1]), px[2])));
+        int min_y = f2i(floorf(rmin(rmin(py[0], py[1]), py[2])));
+        int max_y = f2i(ceilf(rmax(rmax(py[0], py[1]), py[2])));
+        min_x = imax(min_x, 0); max_x = imin(max_x, tg->W - 1);
+        min_y = imax(min_y, 0); max_y = imin(max_y, tg->H - 1);
+        const int tx1 = tg->rx0 + tg->rw - 1, ty1 = tg->ry0 + tg->rh - 1;
+        min_x = imax(min_x, tg->rx0); max_x = imin(max_x, tx1);
+        min_y = imax(min_y, tg->ry0); max_y = imin(max_y, ty1);
+        if (min_x > max_x || min_y > max_y) continue;
+        const float area = edge_function(px[0], py[0], px[1], py[1], px[2], py[2]);
+        if (area <= 0.0f) continue;
+        if (area < 0.1f) continue; /* MIN_TRIANGLE_AREA :1998 */
+        const float inv_area = 1.0f / area;
+        const float e0dx = py[2] - py[1], e0dy = px[1] - px[2];
+        const float e1dx = py[0] - py[2], e1dy = px[2] - px[0];
+        const float e2dx = py[1] - py[0], e2dy = px[0] - px[1];
+        const float inv_w0 = 1.0f / w0c, inv_w1 = 1.0f / w1c, inv_w2 = 1.0f / w2c;
+        const float u0w = tri[0].uv[0] * inv_w0, u1w = tri[1].uv[0] * inv_w1, u2w = tri[2].uv[0] * inv_w2;
+        const float v0w = tri[0].uv[1] * inv_w0, v1w = tri[1].uv[1] * inv_w1, v2w = tri[2].uv[1] * inv_w2;
+        const float sx = (float)min_x + 0.5f, sy = (float)min_y + 0.5f;
+        float w0_row = edge_function(px[1], py[1], px[2], py[2], sx, sy);
+        float w1_row = edge_function(px[2], py[2], px[0], py[0], sx, sy);
+        float w2_row = edge_function(px[0], py[0], px[1], py[1], sx, sy);
+        for (int y = min_y; y <= max_y; ++y) {
+            float w0 = w0_row, w1 = w1_row, w2 = w2_row;
+            for (int x = min_x; x <= max_x; ++x) {
+                if (w0 >= 0.0f && w1 >= 0.0f && w2 >= 0.0f) {
+                    const float bw0 = w0 * inv_area, bw1 = w1 * inv_area, bw2 = w2 * inv_area;
+                    const float depth = bw0 * z0 + bw1 * z1 + bw2 * z2;
+                    size_t idx = (size_t)y * (size_t)tg->W + (size_t)x;
+                    if (depth < tg->depth[idx]) {
+                        tg->depth[idx] = depth;
+                        const float inv_w_interp = bw0 * inv_w0 + bw1 * inv_w1 + bw2 * inv_w2;
+                        const float u = (bw0 * u0w + bw1 * u1w + bw2 * u2w) / inv_w_interp;
+                        const float v = (bw0 * v0w + bw1 * v1w + bw2 * v2w) / inv_w_interp;
+                        uint8_t tex_u = (uint8_t)(f2i(u * 8.0f) & 7);
+                        uint8_t tex_v = (uint8_t)(f2i(v * 8.0f) & 7);
+                        uint32_t c = vxo_texture_sample(tg->atlas, tex_id, tex_u, tex_v);
+                        if (tg->cfg->enable_shading) c = vxo_shade_color_u32(c, light);
+                        tg->color[idx] = c;
+                    }
+                }
+                w0 += e0dx; w1 += e1dx; w2 += e2dx;
+            }
+            w0_row += e0dy; w1_row += e1dy; w2_row += e2dy;
+        }
+    }
+}
+
 /* vertex table rasterizer.rs:1092-1129 (== mesh.rs:624-661); `u + w` is u8 arithmetic. */
 static void quad_local_positions(int face, uint8_t s, uint8_t u, uint8_t v, uint8_t w, uint8_t h, float lp[4][3], float uv[4][2]) {
     float fs = (float)s, u0 = (float)u, v0 = (float)v, u1 = (float)(uint8_t)(u + w), v1 = (float)(uint8_t)(v + h);
@@ -670,7 +755,8 @@ static void render_tiny_quad_span(const uint8_t q3[3], int face, uint8_t slice_p
     static const int tri_idx[2][3] = {{0, 1, 2}, {0, 2, 3}};
     for (int t = 0; t < 2; ++t) {
         clip_vtx tri[3] = {cv[tri_idx[t][0]], cv[tri_idx[t][1]], cv[tri_idx[t][2]]};
-        render_triangle_span_from_clip(tri, bt, light, tg);
+        if (tg->barycentric) render_triangle_from_clip_textured(tri, bt, light, tg); /* render_tiny_quad :932-1071 (same tables) */
+        else render_triangle_span_from_clip(tri, bt, light, tg);
     }
 }
 
@@ -721,7 +807,24 @@ static void render_mesh_tiny_quads(const vxo_mesh_batch *mb, int32_t id, const f
 
 void vxo_render_mesh(const vxo_mesh_batch *mb, int32_t mesh_id, const float vp[16], const vxo_frame_config *cfg,
                      const vxo_atlas *atlas, const int32_t rect[4], uint32_t *color, float *depth) {
-    target_t tg = {cfg->width, cfg->height, rect[0], rect[1], rect[2], rect[3], color, depth, cfg, atlas};
+    target_t tg = {cfg->width, cfg->height, rect[0], rect[1], rect[2], rect[3], color, depth, cfg, atlas, 0};
+    render_mesh_tiny_quads(mb, mesh_id, vp, &tg);
+}
+
+/* Rasterizer::render_mesh_tiny_quads(mesh, vp, target, use_span_renderer) rasterizer.rs:782-929 */
+void vxo_render_mesh_tiny_quads(const vxo_mesh_batch *mb, int32_t mesh_id, const float vp[16], const vxo_frame_config *cfg,
+                                const vxo_atlas *atlas, const int32_t rect[4], int32_t use_span_renderer, uint32_t *color,
+                                float *depth) {
+    target_t tg = {cfg->width, cfg->height, rect[0], rect[1], rect[2], rect[3], color, depth, cfg, atlas, use_span_renderer ? 0 : 1};
+    render_mesh_tiny_quads(mb, mesh_id, vp, &tg);
+}
+
+/* Rasterizer::render_mesh_with_up rasterizer.rs:399-411 + is_camera_level :377-382: whole framebuffer; the span
+ * renderer only when the camera is level (|up.y| >= 0.995). */
+void vxo_render_mesh_with_up(const vxo_mesh_batch *mb, int32_t mesh_id, const float vp[16], const vxo_frame_config *cfg,
+                             const vxo_atlas *atlas, const float camera_up[3], uint32_t *color, float *depth) {
+    const int level = fabsf(camera_up[1]) >= 0.995f;
+    target_t tg = {cfg->width, cfg->height, 0, 0, cfg->width, cfg->height, color, depth, cfg, atlas, level ? 0 : 1};
     render_mesh_tiny_quads(mb, mesh_id, vp, &tg);
 }
 

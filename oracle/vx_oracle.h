@@ -121,6 +121,15 @@ uint32_t vxo_texture_sample(const vxo_atlas *a, int tex, uint8_t u, uint8_t v); 
 void vxo_render_mesh(const vxo_mesh_batch *mb, int32_t mesh_id, const float vp[16], const vxo_frame_config *cfg,
                      const vxo_atlas *atlas, const int32_t rect[4], uint32_t *color, float *depth);
 
+/* Rasterizer::render_mesh_tiny_quads rasterizer.rs:782-929 with the pub use_span_renderer switch: 0 = the barycentric
+ * rasterizer render_triangle_from_clip_textured (:1881-2107). */
+void vxo_render_mesh_tiny_quads(const vxo_mesh_batch *mb, int32_t mesh_id, const float vp[16], const vxo_frame_config *cfg,
+                                const vxo_atlas *atlas, const int32_t rect[4], int32_t use_span_renderer, uint32_t *color,
+                                float *depth);
+/* Rasterizer::render_mesh_with_up rasterizer.rs:399-411 (span renderer iff |camera_up.y| >= 0.995, :377-382). */
+void vxo_render_mesh_with_up(const vxo_mesh_batch *mb, int32_t mesh_id, const float vp[16], const vxo_frame_config *cfg,
+                             const vxo_atlas *atlas, const float camera_up[3], uint32_t *color, float *depth);
+
 /* main.rs:283-297 + :368-377 + render_frame :379-608 (occlusion off).
  *   mesh_ids: chunks that passed filter A and have a mesh, in caller order
  *   survivors_out: draw order after filter B + sorts;  returns survivor count

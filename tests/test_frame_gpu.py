@@ -538,3 +538,99 @@ def test_macrotile_frame_empty_list_and_colour_only(ctx, ob, scene5):
     oc = ob.render_frame_macrotile(ref, ids, cam.view_projection(), ob.default_frame_config(320, 200), ob.default_atlas())[0]
     color, depth, proj = api.render_frame_macrotile(batch, ids, cam.view_projection(), cfg, want_tile_depth=False, ctx=ctx)
     assert depth is None and np.array_equal(color, oc)
+
+
+# ---- barycentric mesh path (render_mesh_with_up / render_mesh_tiny_quads(.., false), rasterizer.rs:399, :782, :1881) ------
+def _rolled_vp(eye, center, up, w, h):
+    proj = camera.perspective_rh(np.radians(np.float32(70.0)), w / h, 0.1, 1000.0)
+    return camera.mat4_mul(proj, camera.look_at_rh(eye, center, up)).reshape(16)
+
+
+def test_barycentric_reference_kat_and_level_switch(ctx, ob):
+    """tests/rendering_pipeline_tests.rs:75-127 through the C ABI, bit-exact against the oracle for both up vectors."""
+    vox = np.zeros((32, 32, 32), dtype=np.uint8)
+    vox[:, 0, :] = 1
+    batch = api.BinaryGreedyMesher.mesh_batch(vox.reshape(1, -1), [(0, 0, 0)], None, None, ctx)
+    ref = ob.mesh_chunks(vox.reshape(1, -1))
+    w, h, clear = 256, 192, 0xFF000000
+    cam = camera.Camera((16.0, 40.0, 80.0), w / h)
+    vp = cam.view_projection()
+    ocfg, atlas = ob.default_frame_config(w, h), ob.default_atlas()
+    r = api.Rasterizer(ctx)
+    rows = {}
+    for up in ((0.0, 0.0, 1.0), (0.05, 0.998, 0.0), (0.0, 0.99, 0.1)):
+        fb = api.Framebuffer(w, h)
+        fb.clear(clear)
+        oc, od = fb.color_buffer.copy(), fb.depth_buffer.copy()
+        ob.render_mesh_with_up(ref, 0, vp, ocfg, atlas, up, oc, od)
+        r.render_mesh_with_up(batch, 0, vp, fb, up)
+        assert np.array_equal(fb.color_buffer, oc) and np.array_equal(fb.depth_buffer.view(np.uint32), od.view(np.uint32)), up
+        rows[up] = (fb.color_buffer != clear).any(axis=1)
+    assert rows[(0.0, 0.0, 1.0)].any() and np.array_equal(rows[(0.0, 0.0, 1.0)], rows[(0.05, 0.998, 0.0)])
+    batch.release()
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_barycentric_terrain_meshes_bit_exact(ctx, ob, scene5, case):
+    """Terrain meshes through render_mesh_tiny_quads(.., use_span_renderer = false): rolled cameras, a camera inside the
+    terrain (near clipping), tile / stripe targets, several meshes accumulated into one framebuffer (equal depth keeps
+    the first), backface culling and shading off."""
+    _, p, batch, ref = scene5
+    w, h = (320, 200) if case != 3 else (641, 353)
+    ids = np.flatnonzero(ref.has_mesh != 0)
+    if case in (0, 1):
+        cam = vx_scenes.path_camera(case, w, h)
+        vp = cam.view_projection()
+    elif case == 2:
+        vp = _rolled_vp((20.0, 30.0, 40.0), (0.0, 0.0, 0.0), (0.6, 0.8, 0.0), w, h)       # 37 degree roll
+    elif case == 3:
+        vp = _rolled_vp((-30.0, 12.0, 25.0), (10.0, 0.0, -10.0), (0.0, 0.2, 1.0), w, h)   # nearly sideways
+    elif case == 4:
+        vp = vx_scenes.path_camera(5, w, h).view_projection()                             # inside the terrain
+    else:
+        vp = vx_scenes.path_camera(3, w, h).view_projection()                             # looking down
+    rects = [(0, 0, w, h)] if case != 1 else [(0, 0, w, 64), (0, 64, w, h - 64)]
+    if case == 5:
+        rects = [(17, 9, 200, 150)]
+    ocfg, atlas = ob.default_frame_config(w, h), ob.default_atlas()
+    r = api.Rasterizer(ctx)
+    if case == 4:
+        ocfg.backface_culling = 0
+        r.backface_culling = False
+    if case == 5:
+        ocfg.enable_shading = 0
+        r.enable_shading = False
+    fb = api.Framebuffer(w, h)
+    fb.clear(0xFF87CEEB)
+    fb.depth_buffer[40:60, 50:150] = 0.9  # existing contents take part in the depth test
+    fb.color_buffer[40:60, 50:150] = 0xFF010203
+    oc, od = fb.color_buffer.copy(), fb.depth_buffer.copy()
+    for k, mesh_id in enumerate(ids.tolist()):
+        for rect in rects:
+            ob.render_mesh_tiny_quads(ref, mesh_id, vp, ocfg, atlas, rect, False, oc, od)
+            r.render_mesh_tiny_quads(batch, mesh_id, vp, fb, rect, False)
+        if k % 8 == 0 or k == ids.size - 1:
+            assert np.array_equal(fb.depth_buffer.view(np.uint32), od.view(np.uint32)), f"depth differs after mesh {mesh_id}"
+            assert np.array_equal(fb.color_buffer, oc), f"colour differs after mesh {mesh_id}"
+    assert int((oc != 0xFF87CEEB).sum()) > 2000
+
+
+def test_barycentric_use_span_flag_and_bad_arguments(ctx, ob, scene5):
+    _, p, batch, ref = scene5
+    w, h = 256, 160
+    vp = vx_scenes.path_camera(1, w, h).view_projection()
+    mesh_id = int(np.flatnonzero(ref.has_mesh != 0)[3])
+    r = api.Rasterizer(ctx)
+    a, b = api.Framebuffer(w, h), api.Framebuffer(w, h)
+    r.render_mesh_tiny_quads(batch, mesh_id, vp, a, (0, 0, w, h), True)   # use_span_renderer = true == render_mesh
+    r.render_mesh(batch, mesh_id, vp, b)
+    assert np.array_equal(a.color_buffer, b.color_buffer) and np.array_equal(a.depth_buffer.view(np.uint32), b.depth_buffer.view(np.uint32))
+    no_mesh = int(np.flatnonzero(ref.has_mesh == 0)[0]) if (ref.has_mesh == 0).any() else None
+    if no_mesh is not None:  # mesh.is_empty(): nothing happens
+        c = api.Framebuffer(w, h)
+        r.render_mesh_tiny_quads(batch, no_mesh, vp, c, (0, 0, w, h), False)
+        assert (c.color_buffer == 0).all() and np.isinf(c.depth_buffer).all()
+    with pytest.raises(api.VxError):
+        r.render_mesh_tiny_quads(batch, mesh_id, vp, a, (10, 10, w, h), False)  # rect leaves the framebuffer
+    with pytest.raises(api.VxError):
+        r.render_mesh_tiny_quads(batch, 10**6, vp, a, (0, 0, w, h), False)

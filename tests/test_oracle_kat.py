@@ -548,3 +548,60 @@ def test_macrotile_frame_covers_the_same_pixels_as_the_stripe_frame(ob):
         for i in list(proj1[kinds1 == 1]) + list(proj1[kinds1 == 2]):
             ob.render_mesh(mb, int(i), vp1, cfg1, atlas, (0, 0, 100, 90), c3, d3)
         assert np.array_equal(c1, c3) and np.array_equal(d1.view(np.uint32), d3.view(np.uint32))
+
+
+# ---- barycentric mesh path: tests/rendering_pipeline_tests.rs:75-127 --------------------------------------------------
+def _row_coverage(color, clear):
+    return (color != clear).any(axis=1)
+
+
+def test_span_renderer_matches_barycentric_row_coverage(ob):
+    """A 32 x 32 Grass floor (y = 0) seen from (16, 40, 80) at 256 x 192: render_mesh (span renderer) and
+    render_mesh_with_up with the non-level up vector (0, 0, 1) (barycentric renderer) cover the same scanlines."""
+    from differential_projection_voxel_renderer_b200 import camera
+    vox = np.zeros((32, 32, 32), dtype=np.uint8)  # [z][y][x]
+    vox[:, 0, :] = 1
+    mb = ob.mesh_chunks(vox.reshape(1, -1))
+    w, h, clear = 256, 192, 0xFF000000
+    cam = camera.Camera((16.0, 40.0, 80.0), w / h)
+    vp = cam.view_projection()
+    cfg = ob.default_frame_config(w, h)
+    atlas = ob.default_atlas()
+    span_c = np.full((h, w), clear, dtype=np.uint32); span_d = np.full((h, w), np.inf, dtype=np.float32)
+    ref_c = span_c.copy(); ref_d = span_d.copy()
+    ob.render_mesh(mb, 0, vp, cfg, atlas, (0, 0, w, h), span_c, span_d)
+    ob.render_mesh_with_up(mb, 0, vp, cfg, atlas, (0.0, 0.0, 1.0), ref_c, ref_d)
+    assert _row_coverage(span_c, clear).any()
+    assert np.array_equal(_row_coverage(span_c, clear), _row_coverage(ref_c, clear))
+    # a level up vector takes the span renderer: bit-identical to render_mesh (is_camera_level, rasterizer.rs:377-382)
+    lvl_c = np.full((h, w), clear, dtype=np.uint32); lvl_d = np.full((h, w), np.inf, dtype=np.float32)
+    ob.render_mesh_with_up(mb, 0, vp, cfg, atlas, (0.05, 0.998, 0.0), lvl_c, lvl_d)
+    assert np.array_equal(lvl_c, span_c) and np.array_equal(lvl_d.view(np.uint32), span_d.view(np.uint32))
+    # and the two renderers agree on nearly every pixel (same triangles, different interpolation arithmetic)
+    assert float((ref_c != span_c).mean()) < 0.01
+    both = np.isfinite(ref_d) & np.isfinite(span_d)
+    assert float(np.abs(ref_d[both] - span_d[both]).max()) < 1e-4
+
+
+def test_barycentric_target_rects_partition_the_frame_coverage(ob):
+    """Unlike the span renderer the barycentric one restarts its edge-function chains at every target's box corner, so
+    tiles are not bit-identical to the full frame -- but the covered pixel set is the same up to the rounding of those
+    chains on exact edges, and every tile only writes inside its rect."""
+    from differential_projection_voxel_renderer_b200 import camera
+    mb = _one_quad_batch(ob, kat.chunk_slab())
+    w, h = 200, 150
+    cam = camera.Camera((16, 40, 80), w / h)
+    vp = cam.view_projection()
+    cfg = ob.default_frame_config(w, h)
+    atlas = ob.default_atlas()
+    full_c = np.full((h, w), cfg.clear_color, dtype=np.uint32); full_d = np.full((h, w), np.inf, dtype=np.float32)
+    ob.render_mesh_tiny_quads(mb, 0, vp, cfg, atlas, (0, 0, w, h), False, full_c, full_d)
+    tile_c = np.full((h, w), cfg.clear_color, dtype=np.uint32); tile_d = np.full((h, w), np.inf, dtype=np.float32)
+    for (x0, y0, tw, th) in ((0, 0, 100, 75), (100, 0, 100, 75), (0, 75, 100, 75), (100, 75, 100, 75)):
+        before = tile_c.copy()
+        ob.render_mesh_tiny_quads(mb, 0, vp, cfg, atlas, (x0, y0, tw, th), False, tile_c, tile_d)
+        changed = tile_c != before
+        changed[y0:y0 + th, x0:x0 + tw] = False
+        assert not changed.any()
+    assert int((full_c != cfg.clear_color).sum()) > 1000
+    assert float(((tile_c != cfg.clear_color) != (full_c != cfg.clear_color)).mean()) < 0.002
