@@ -41,7 +41,9 @@ class VxFrameConfig(C.Structure):
                 ("light_dir", C.c_float * 3), ("ambient", C.c_float), ("diffuse", C.c_float),
                 ("stripe_y0", C.c_int32), ("stripe_rows", C.c_int32),
                 ("differential_projection", C.c_int32), ("async_submit", C.c_int32),
-                ("profile_kernels", C.c_int32), ("macrotile", C.c_int32)]
+                ("profile_kernels", C.c_int32), ("macrotile", C.c_int32),
+                ("occlusion_culling", C.c_int32), ("occlusion_grid_w", C.c_int32), ("occlusion_grid_h", C.c_int32),
+                ("reserved", C.c_int32 * 1)]
 
 
 class VxTerrainParams(C.Structure):

@@ -82,6 +82,9 @@ void vx_default_frame_config(VxFrameConfig *cfg, int32_t width, int32_t height) 
     cfg->ambient = 0.35f;
     cfg->diffuse = 0.65f;
     cfg->differential_projection = 0;
+    cfg->occlusion_culling = 0;     // main.rs:112
+    cfg->occlusion_grid_w = 128;    // main.rs:46-47
+    cfg->occlusion_grid_h = 72;
 }
 
 static uint32_t rgb565_to_argb32(uint16_t c) { // texture.rs:42-54

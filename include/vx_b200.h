@@ -99,6 +99,14 @@ typedef struct {
      * restarts at the column's first pixel (rasterizer.rs:1404-1432 with rect_x0 = the tile's x0).
      * profile_kernels = 2 acts like 1 in this mode. */
     int32_t macrotile;
+    /* 1: the chunk-level occlusion pass of render_frame (main.rs:501-526 over OcclusionBuffer, occlusion.rs:60-153;
+     * off in the reference's default run, main.rs:112): survivors front to back, a mesh at least two chunks away whose
+     * every grid cell already holds a depth nearer than near_depth - 0.005 is dropped, every other one marks its
+     * screen rect into the grid at its near depth.  Grid = occlusion_grid_w x occlusion_grid_h cells over the full
+     * frame (128 x 72, main.rs:46-47; at most 12288 cells).  Ignored by vx_render_mesh and in macrotile mode. */
+    int32_t occlusion_culling;
+    int32_t occlusion_grid_w, occlusion_grid_h;
+    int32_t reserved[1];
 } VxFrameConfig;
 
 typedef struct {

@@ -33,7 +33,8 @@ class FrameConfig(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("clear_color", C.c_uint32),
                 ("backface_culling", C.c_int32), ("enable_shading", C.c_int32),
                 ("light_dir", C.c_float * 3), ("ambient", C.c_float), ("diffuse", C.c_float),
-                ("n_threads", C.c_int32)]
+                ("n_threads", C.c_int32), ("occlusion_culling", C.c_int32), ("occlusion_grid_w", C.c_int32),
+                ("occlusion_grid_h", C.c_int32)]
 
 
 class MeshBatchView(C.Structure):

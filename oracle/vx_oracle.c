@@ -420,6 +420,8 @@ void vxo_default_frame_config(vxo_frame_config *cfg, int w, int h) {
     cfg->light_dir[0] = 0.35634832f; cfg->light_dir[1] = 0.8908708f; cfg->light_dir[2] = 0.2672612f;
     cfg->ambient = 0.35f; cfg->diffuse = 0.65f;
     cfg->n_threads = 1;
+    cfg->occlusion_culling = 0;     /* main.rs:112 */
+    cfg->occlusion_grid_w = 128; cfg->occlusion_grid_h = 72; /* main.rs:46-47 */
 }
 
 /* shading.rs:90-110 */
@@ -856,7 +858,42 @@ static void *stripe_worker(void *arg) {
     return NULL;
 }
 
-/* main.rs:283-297, :368-377, :379-608 (occlusion pass disabled as main.rs:112) */
+/* OcclusionBuffer occlusion.rs:6-154 (the parts render_frame uses) */
+typedef struct { int sw, sh, gw, gh; float *cells; } occlusion_buffer;
+
+static int occ_clamp_rect(const occlusion_buffer *o, int *min_x, int *min_y, int *max_x, int *max_y) {
+    if (o->sw == 0 || o->sh == 0) return 0;
+    if (*max_x < 0 || *max_y < 0 || *min_x >= o->sw || *min_y >= o->sh) return 0;
+    *min_x = imax(*min_x, 0); *min_y = imax(*min_y, 0);
+    *max_x = imin(*max_x, o->sw - 1); *max_y = imin(*max_y, o->sh - 1);
+    return !(*min_x > *max_x || *min_y > *max_y);
+}
+
+/* occlusion.rs:60-99 */
+static void occ_mark_rect(occlusion_buffer *o, int min_x, int min_y, int max_x, int max_y, float depth) {
+    if (!occ_clamp_rect(o, &min_x, &min_y, &max_x, &max_y)) return;
+    int cx0 = (int)(((int64_t)min_x * o->gw) / o->sw), cx1 = (int)(((int64_t)max_x * o->gw) / o->sw);
+    int cy0 = (int)(((int64_t)min_y * o->gh) / o->sh), cy1 = (int)(((int64_t)max_y * o->gh) / o->sh);
+    for (int cy = cy0; cy <= cy1; ++cy)
+        for (int cx = cx0; cx <= cx1; ++cx) {
+            float *cell = &o->cells[cy * o->gw + cx];
+            if (depth < *cell) *cell = depth;
+        }
+}
+
+/* occlusion.rs:105-153 */
+static int occ_is_occluded(const occlusion_buffer *o, int min_x, int min_y, int max_x, int max_y, float near_depth) {
+    if (!occ_clamp_rect(o, &min_x, &min_y, &max_x, &max_y)) return 0;
+    int cx0 = (int)(((int64_t)min_x * o->gw) / o->sw), cx1 = (int)(((int64_t)max_x * o->gw) / o->sw);
+    int cy0 = (int)(((int64_t)min_y * o->gh) / o->sh), cy1 = (int)(((int64_t)max_y * o->gh) / o->sh);
+    const float epsilon = 0.005f;
+    for (int cy = cy0; cy <= cy1; ++cy)
+        for (int cx = cx0; cx <= cx1; ++cx)
+            if (!(o->cells[cy * o->gw + cx] < near_depth - epsilon)) return 0;
+    return 1;
+}
+
+/* main.rs:283-297, :368-377, :379-608 (occlusion pass :501-526 when cfg->occlusion_culling, off by default as main.rs:112) */
 int vxo_render_frame(const vxo_mesh_batch *mb, const int32_t *mesh_ids, int32_t n_meshes, const float vp[16],
                      const float cam_pos[3], const vxo_frame_config *cfg, const vxo_atlas *atlas,
                      uint32_t *color, float *depth, int32_t *survivors_out) {
@@ -889,6 +926,8 @@ int vxo_render_frame(const vxo_mesh_batch *mb, const int32_t *mesh_ids, int32_t 
     float *near_depth = (float *)malloc(sizeof(float) * (size_t)n_meshes);
     int32_t *proj = (int32_t *)malloc(sizeof(int32_t) * (size_t)n_meshes);
     int32_t *rect_y = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)n_meshes);
+    int32_t *rect_x = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)n_meshes);
+    uint8_t *use_occ = (uint8_t *)malloc((size_t)n_meshes);
     int32_t n_proj = 0;
     for (int32_t oi = 0; oi < n_meshes; ++oi) {
         int32_t i = order[oi];
@@ -924,6 +963,11 @@ int vxo_render_frame(const vxo_mesh_batch *mb, const int32_t *mesh_ids, int32_t 
         }
         near_depth[n_proj] = nd;
         rect_y[2 * n_proj] = rect_min_y; rect_y[2 * n_proj + 1] = rect_max_y;
+        rect_x[2 * n_proj] = rect_min_x; rect_x[2 * n_proj + 1] = rect_max_x;
+        { /* main.rs:473-478: OCCLUSION_MIN_DISTANCE_CHUNKS = 2 */
+            const float t = (float)CS * 2.0f;
+            use_occ[n_proj] = (uint8_t)(cfg->occlusion_culling && dist_sq[i] >= t * t);
+        }
         proj[n_proj] = i;
         n_proj++;
     }
@@ -931,6 +975,21 @@ int vxo_render_frame(const vxo_mesh_batch *mb, const int32_t *mesh_ids, int32_t 
     int32_t *ord2 = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_proj > 0 ? n_proj : 1));
     for (int32_t i = 0; i < n_proj; ++i) ord2[i] = i;
     stable_sort_by_key(ord2, n_proj, near_depth);
+    if (cfg->occlusion_culling) { /* 2. occlusion pass main.rs:501-526, serial front to back */
+        occlusion_buffer occ = {W, H, cfg->occlusion_grid_w, cfg->occlusion_grid_h, NULL};
+        const size_t nc = (size_t)imax(occ.gw, 0) * (size_t)imax(occ.gh, 0);
+        occ.cells = (float *)malloc(sizeof(float) * (nc ? nc : 1));
+        for (size_t i = 0; i < nc; ++i) occ.cells[i] = INFINITY; /* occlusion.clear() main.rs:394 */
+        int32_t kept = 0;
+        for (int32_t i = 0; i < n_proj; ++i) {
+            const int32_t pj = ord2[i];
+            if (use_occ[pj] && occ_is_occluded(&occ, rect_x[2 * pj], rect_y[2 * pj], rect_x[2 * pj + 1], rect_y[2 * pj + 1], near_depth[pj])) continue;
+            occ_mark_rect(&occ, rect_x[2 * pj], rect_y[2 * pj], rect_x[2 * pj + 1], rect_y[2 * pj + 1], near_depth[pj]);
+            ord2[kept++] = pj;
+        }
+        n_proj = kept;
+        free(occ.cells);
+    }
     for (int32_t i = 0; i < n_proj; ++i) survivors_out[i] = mesh_ids[proj[ord2[i]]];
 
     /* 3. stripe binning main.rs:528-557, 4. stripe rendering :559-597.  Rayon's
@@ -953,7 +1012,7 @@ int vxo_render_frame(const vxo_mesh_batch *mb, const int32_t *mesh_ids, int32_t 
         for (int t = 0; t < thread_count; ++t) pthread_join(th[t], NULL);
         free(th);
     }
-    free(center); free(dist_sq); free(order); free(near_depth); free(proj); free(rect_y); free(ord2);
+    free(center); free(dist_sq); free(order); free(near_depth); free(proj); free(rect_y); free(rect_x); free(use_occ); free(ord2);
     return n_proj;
 }
 

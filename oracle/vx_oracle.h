@@ -97,6 +97,8 @@ typedef struct {
     float light_dir[3];       /* shading.rs:21-31 */
     float ambient, diffuse;
     int32_t n_threads;        /* stripes = 4*n_threads, main.rs:531-534 */
+    int32_t occlusion_culling; /* main.rs:112 (off), :501-526 */
+    int32_t occlusion_grid_w, occlusion_grid_h; /* main.rs:46-47: 128 x 72 */
 } vxo_frame_config;
 
 typedef struct {

@@ -40,13 +40,14 @@ def test_python_prototypes_cover_the_header():
 def test_struct_layouts_match_the_header():
     from differential_projection_voxel_renderer_b200 import _lib
     assert ctypes.sizeof(_lib.VxAtlas) == 4 * 16 * 4 + 4 * 32
-    assert ctypes.sizeof(_lib.VxFrameConfig) == 16 * 4
+    assert ctypes.sizeof(_lib.VxFrameConfig) == 20 * 4
     assert ctypes.sizeof(_lib.VxMeshBatchInfo) == 16
     assert ctypes.sizeof(_lib.VxFrameStats) == 32
     lib = _lib.load()
     cfg = _lib.VxFrameConfig()
     lib.vx_default_frame_config(ctypes.byref(cfg), 1280, 720)  # host-only helper
     assert (cfg.width, cfg.height, cfg.clear_color, cfg.backface_culling, cfg.enable_shading) == (1280, 720, 0xFF87CEEB, 1, 1)
+    assert (cfg.macrotile, cfg.occlusion_culling, cfg.occlusion_grid_w, cfg.occlusion_grid_h) == (0, 0, 128, 72)  # main.rs:46-47, :112
     a = _lib.VxAtlas()
     lib.vx_default_atlas(ctypes.byref(a))
     assert a.palette[1][0] == 0xFF007D00

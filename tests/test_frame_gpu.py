@@ -634,3 +634,66 @@ def test_barycentric_use_span_flag_and_bad_arguments(ctx, ob, scene5):
         r.render_mesh_tiny_quads(batch, mesh_id, vp, a, (10, 10, w, h), False)  # rect leaves the framebuffer
     with pytest.raises(api.VxError):
         r.render_mesh_tiny_quads(batch, 10**6, vp, a, (0, 0, w, h), False)
+
+
+# ---- chunk-level occlusion pass (main.rs:501-526, occlusion.rs:60-153) -----------------------------------
+@pytest.mark.parametrize("cam_i,grid", [(0, (128, 72)), (1, (128, 72)), (3, (128, 72)), (3, (16, 9)), (5, (128, 72)), (2, (64, 36))])
+def test_frame_with_occlusion_pass_bit_exact(ctx, ob, scene5, cam_i, grid):
+    """cfg.occlusion_culling = 1: the serial front-to-back pass drops the same meshes as the oracle, so survivors, depth and
+    colour stay bit-identical; vx_frame_stats reports the post-occlusion survivor count."""
+    _, p, batch, ref = scene5
+    w, h = 640, 360
+    cam = vx_scenes.path_camera(cam_i, w, h)
+    vp = cam.view_projection()
+    vis = ob.cull_chunks(p, vp, cam.position, 5)
+    ids = np.flatnonzero((vis != 0) & (ref.has_mesh != 0)).astype(np.int32)
+    ocfg = ob.default_frame_config(w, h, n_threads=4)
+    ocfg.occlusion_culling = 1
+    ocfg.occlusion_grid_w, ocfg.occlusion_grid_h = grid
+    oc, od, osurv = ob.render_frame(ref, ids, vp, cam.position, ocfg, ob.default_atlas())
+    cfg = api.default_frame_config(w, h)
+    assert (cfg.occlusion_grid_w, cfg.occlusion_grid_h) == (128, 72)
+    cfg.occlusion_culling = 1
+    cfg.occlusion_grid_w, cfg.occlusion_grid_h = grid
+    color, depth, surv = api.render_frame(batch, vp, cam.position, cfg, mesh_ids=ids, ctx=ctx)
+    assert np.array_equal(surv, osurv), "the occlusion pass kept a different set / order of meshes"
+    assert np.array_equal(depth.view(np.uint32), od.view(np.uint32)) and np.array_equal(color, oc)
+    assert api.frame_stats(ctx).n_survivors == osurv.size
+    # device-side filter A in front of it gives the same frame
+    color2, depth2, surv2 = api.render_frame(batch, vp, cam.position, cfg, mesh_ids=None, view_distance=5, ctx=ctx)
+    assert np.array_equal(surv2, osurv) and np.array_equal(color2, oc)
+    # and switching the pass off again restores the plain frame (no state leaks between frames)
+    cfg.occlusion_culling = 0
+    _, _, oc0, od0, osurv0 = oracle_frame(ob, ref, p, cam, w, h, 5)
+    color3, depth3, surv3 = api.render_frame(batch, vp, cam.position, cfg, mesh_ids=ids, ctx=ctx)
+    assert np.array_equal(surv3, osurv0) and np.array_equal(color3, oc0) and np.array_equal(depth3.view(np.uint32), od0.view(np.uint32))
+
+
+def test_occlusion_pass_full_frame_vd12_and_bad_grid(ctx, ob):
+    pos, world, p, v, nb = vx_scenes.terrain_scene(12)
+    batch = api.BinaryGreedyMesher.mesh_batch(v, p, nb, None, ctx)
+    ref = ob.mesh_chunks(v, nb, None, p)
+    w, h = 1280, 720
+    dropped = 0
+    for cam_i in (0, 3):
+        cam = vx_scenes.path_camera(cam_i, w, h)
+        vp = cam.view_projection()
+        vis = ob.cull_chunks(p, vp, cam.position, 12)
+        ids = np.flatnonzero((vis != 0) & (ref.has_mesh != 0)).astype(np.int32)
+        ocfg = ob.default_frame_config(w, h, n_threads=8)
+        plain = ob.render_frame(ref, ids, vp, cam.position, ocfg, ob.default_atlas())[2]
+        ocfg.occlusion_culling = 1
+        oc, od, osurv = ob.render_frame(ref, ids, vp, cam.position, ocfg, ob.default_atlas())
+        cfg = api.default_frame_config(w, h)
+        cfg.occlusion_culling = 1
+        color, depth, surv = api.render_frame(batch, vp, cam.position, cfg, mesh_ids=None, view_distance=12, ctx=ctx)
+        assert np.array_equal(surv, osurv) and np.array_equal(color, oc) and np.array_equal(depth.view(np.uint32), od.view(np.uint32))
+        dropped += plain.size - osurv.size
+    assert dropped > 0
+    cfg.occlusion_grid_w, cfg.occlusion_grid_h = 0, 72
+    with pytest.raises(api.VxError):
+        api.render_frame(batch, vp, cam.position, cfg, mesh_ids=None, view_distance=12, ctx=ctx)
+    cfg.occlusion_grid_w, cfg.occlusion_grid_h = 256, 256
+    with pytest.raises(api.VxError):
+        api.render_frame(batch, vp, cam.position, cfg, mesh_ids=None, view_distance=12, ctx=ctx)
+    batch.release()

@@ -605,3 +605,39 @@ def test_barycentric_target_rects_partition_the_frame_coverage(ob):
         assert not changed.any()
     assert int((full_c != cfg.clear_color).sum()) > 1000
     assert float(((tile_c != cfg.clear_color) != (full_c != cfg.clear_color)).mean()) < 0.002
+
+
+# ---- chunk-level occlusion pass: main.rs:473-478, :501-526 over OcclusionBuffer (occlusion.rs:60-153) ----------------
+def test_occlusion_pass_only_drops_far_meshes_and_keeps_the_order(ob):
+    """No reference test exercises the pass (it is off in the default run, main.rs:112); these are the properties its code
+    guarantees: survivors are a subsequence of the un-occluded draw order, meshes nearer than two chunks are never
+    dropped, the first mesh drawn is never dropped, and with the pass off the frame is unchanged."""
+    import vx_scenes
+    pos, world, p, v, nb = vx_scenes.terrain_scene(5)
+    mb = ob.mesh_chunks(v, nb, None, p)
+    w, h = 320, 180
+    atlas = ob.default_atlas()
+    dropped_any = False
+    for cam_i in range(len(vx_scenes.CAMERA_PATH)):
+        cam = vx_scenes.path_camera(cam_i, w, h)
+        vp = cam.view_projection()
+        vis = ob.cull_chunks(p, vp, cam.position, 5)
+        ids = np.flatnonzero((vis != 0) & (mb.has_mesh != 0)).astype(np.int32)
+        cfg = ob.default_frame_config(w, h)
+        assert (cfg.occlusion_culling, cfg.occlusion_grid_w, cfg.occlusion_grid_h) == (0, 128, 72)
+        c0, d0, s0 = ob.render_frame(mb, ids, vp, cam.position, cfg, atlas)
+        cfg.occlusion_culling = 1
+        c1, d1, s1 = ob.render_frame(mb, ids, vp, cam.position, cfg, atlas)
+        it = iter(s0.tolist())
+        assert all(m in it for m in s1.tolist()), "survivors must be a subsequence of the draw order"
+        if s0.size:
+            assert s1.size and s1[0] == s0[0]
+        centers = (p[s0].astype(np.float32) * np.float32(32) + np.float32(16))
+        dist_sq = ((centers - cam.position.astype(np.float32)) ** 2).sum(axis=1)
+        near = set(s0[dist_sq < 64.0 * 64.0 * 0.999].tolist())
+        assert near <= set(s1.tolist())
+        dropped_any |= s1.size < s0.size
+        # pixels can only change where a dropped mesh would have drawn
+        if s1.size == s0.size:
+            assert np.array_equal(c0, c1) and np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
+    assert dropped_any
