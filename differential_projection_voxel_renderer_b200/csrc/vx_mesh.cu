@@ -541,6 +541,103 @@ int run_mesher(VxContext *ctx, const uint8_t *d_vox, const int32_t *d_nb, const 
     return vx_fail(ctx, VX_ERR_CAPACITY, "mesher output did not fit after regrow");
 }
 
+// one CTA per live chunk: move its quads from the old stream to their place in the compacted one
+__global__ void __launch_bounds__(256) compact_quads_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const uint4 *__restrict__ moves, int n_moves) {
+    for (int m = blockIdx.x; m < n_moves; m += gridDim.x) {
+        const uint4 mv = moves[m]; // old base, new base, count (quads)
+        const uint8_t *s = src + 3 * (size_t)mv.x;
+        uint8_t *d = dst + 3 * (size_t)mv.y;
+        const uint32_t bytes = 3u * mv.z;
+        for (uint32_t i = threadIdx.x; i < bytes; i += blockDim.x) d[i] = s[i];
+    }
+}
+
+// Drop the dead space of an append-updated quad stream WITHOUT re-meshing (the streaming world keeps meshes that are
+// deliberately stale, main.rs:225-280): live quads are copied chunk by chunk into a fresh stream with room for
+// `extra_quads` more.
+int compact_stream(VxContext *ctx, VxMeshBatch *b, int64_t extra_quads) {
+    const size_t n = (size_t)b->n_chunks;
+    std::vector<uint32_t> base(n), count(n);
+    std::vector<uint8_t> has(n);
+    if (n) {
+        VX_CUDA(ctx, cudaMemcpyAsync(base.data(), b->quad_base.ptr, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        VX_CUDA(ctx, cudaMemcpyAsync(count.data(), b->quad_count.ptr, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        VX_CUDA(ctx, cudaMemcpyAsync(has.data(), b->has_mesh.ptr, n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<uint4> moves;
+    uint64_t live = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (has[i] && count[i]) {
+            moves.push_back(make_uint4(base[i], (uint32_t)live, count[i], 0u));
+            base[i] = (uint32_t)live;
+            live += count[i];
+        } else {
+            base[i] = (uint32_t)live;
+        }
+    }
+    const int64_t want = (int64_t)live * 2 + extra_quads + 4096;
+    if (want >= (int64_t)1 << 32) return vx_fail(ctx, VX_ERR_CAPACITY, "more than 2^32 quads in one batch");
+    VxDeviceBuffer fresh;
+    VX_CUDA(ctx, fresh.reserve(3 * (size_t)want + 16));
+    if (!moves.empty()) {
+        VX_CUDA(ctx, ctx->tmp_c.reserve(sizeof(uint4) * moves.size()));
+        VX_CUDA(ctx, cudaMemcpyAsync(ctx->tmp_c.ptr, moves.data(), sizeof(uint4) * moves.size(), cudaMemcpyHostToDevice, ctx->stream));
+        const int grid = (int)(moves.size() < (size_t)ctx->num_sms * 8 ? moves.size() : (size_t)ctx->num_sms * 8);
+        compact_quads_kernel<<<grid, 256, 0, ctx->stream>>>(b->quads.as<uint8_t>(), fresh.as<uint8_t>(), ctx->tmp_c.as<uint4>(), (int)moves.size());
+        VX_CHECK_LAUNCH(ctx);
+    }
+    if (n) VX_CUDA(ctx, cudaMemcpyAsync(b->quad_base.ptr, base.data(), 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned long long h[4] = {live, 0ull, 0ull, 0ull};
+    for (size_t i = 0; i < n; ++i) h[1] += has[i] ? 1 : 0;
+    VX_CUDA(ctx, cudaMemcpyAsync(b->cursor.ptr, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the host vectors above go out of scope
+    b->quads.release();
+    b->quads = fresh;
+    b->cap_quads = want;
+    b->total_quads = (int64_t)live;
+    b->n_meshes = (int32_t)h[1];
+    return VX_OK;
+}
+
+// re-mesh exactly the listed chunks of a world-owning batch in place (append + compaction when the stream is full)
+int remesh_listed(VxContext *ctx, VxMeshBatch *b, const std::vector<int32_t> &list) {
+    if (list.empty()) return VX_OK;
+    const uint8_t *d_vox = b->world_voxels.as<uint8_t>();
+    const int32_t *d_nb = b->has_neighbors ? b->world_neighbors.as<int32_t>() : nullptr;
+    const uint8_t *d_uf = b->world_flags.as<uint8_t>();
+    VxMeshBatchInfo info;
+    int rc = vx_mesh_batch_info(ctx, b, &info);
+    if (rc != VX_OK) return rc;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        const int64_t room = (int64_t)list.size() * (attempt == 0 ? 4096 : 98304); // 98,304 = the most quads a chunk can have
+        if (b->total_quads + room > b->cap_quads) {
+            rc = compact_stream(ctx, b, room);
+            if (rc != VX_OK) return rc;
+        }
+        const int64_t before = b->total_quads; // live end of the stream (run_mesher invalidates the cached value)
+        VX_CUDA(ctx, b->update_ids.reserve(sizeof(int32_t) * list.size()));
+        VX_CUDA(ctx, cudaMemcpyAsync(b->update_ids.ptr, list.data(), sizeof(int32_t) * list.size(), cudaMemcpyHostToDevice, ctx->stream));
+        rc = run_mesher(ctx, d_vox, d_nb, d_uf, b, false, b->update_ids.as<int32_t>(), b->n_chunks, true, (int32_t)list.size());
+        if (rc != VX_OK) return rc;
+        unsigned long long h[4];
+        VX_CUDA(ctx, cudaMemcpyAsync(h, b->cursor.ptr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!h[2]) {
+            b->total_quads = (int64_t)h[0];
+            b->n_meshes = -1;
+            return VX_OK;
+        }
+        // overflow: the chunks of this list that did not fit have no quads; clear the flag, make room, mesh the list again
+        h[2] = 0;
+        h[0] = (unsigned long long)before;
+        VX_CUDA(ctx, cudaMemcpyAsync(b->cursor.ptr, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+        VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        b->total_quads = before;
+    }
+    return vx_fail(ctx, VX_ERR_CAPACITY, "world batch: quad stream overflow persisted");
+}
+
 } // namespace
 
 extern "C" {
@@ -836,6 +933,123 @@ int vx_greedy_mesh_slices(VxContext *ctx, const uint32_t *masks, int32_t n_slice
     VX_CUDA(ctx, cudaMemcpyAsync(out, ctx->tmp_b.ptr, n * 512 * sizeof(VxQuad), cudaMemcpyDeviceToHost, ctx->stream));
     VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VX_OK;
+}
+
+// ---- streaming world: World::update world.rs:57-100 + the mesh cache of main.rs:225-280 -----------------
+
+int vx_world_batch_create(VxContext *ctx, int32_t capacity, VxMeshBatch **out) {
+    if (!ctx || !out || capacity <= 0) return vx_fail(ctx, VX_ERR_INVALID, "vx_world_batch_create: bad argument");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    VxMeshBatch *b = new VxMeshBatch();
+    const size_t n = (size_t)capacity;
+    int rc = batch_alloc(ctx, b, capacity, (int64_t)capacity * 512);
+    cudaError_t e = cudaSuccess;
+    if (rc == VX_OK) e = b->world_voxels.reserve(n * VX_CHUNK_VOLUME + 16);
+    if (rc == VX_OK && e == cudaSuccess) e = b->world_neighbors.reserve(n * 6 * sizeof(int32_t) + 16);
+    if (rc == VX_OK && e == cudaSuccess) e = b->world_flags.reserve(n + 16);
+    if (rc == VX_OK && e == cudaSuccess) { // every slot starts as an absent chunk: no neighbours, "uniform air", no mesh
+        cudaMemsetAsync(b->world_neighbors.ptr, 0xFF, n * 6 * sizeof(int32_t), ctx->stream); // -1 = VX_NBR_NONE
+        cudaMemsetAsync(b->world_flags.ptr, 1, n, ctx->stream);
+        cudaMemsetAsync(b->positions.ptr, 0, sizeof(int32_t) * 3 * n, ctx->stream);
+        cudaMemsetAsync(b->has_mesh.ptr, 0, n, ctx->stream);
+        cudaMemsetAsync(b->quad_count.ptr, 0, sizeof(uint32_t) * n, ctx->stream);
+        cudaMemsetAsync(b->quad_base.ptr, 0, sizeof(uint32_t) * n, ctx->stream);
+        cudaMemsetAsync(b->slice_offsets.ptr, 0, sizeof(uint32_t) * 198 * n, ctx->stream);
+        cudaMemsetAsync(b->face_aabb.ptr, 0, sizeof(int32_t) * 36 * n, ctx->stream);
+        cudaMemsetAsync(b->cursor.ptr, 0, sizeof(unsigned long long) * 4, ctx->stream);
+        e = cudaStreamSynchronize(ctx->stream);
+    }
+    if (rc == VX_OK && e != cudaSuccess) rc = vx_cuda_fail(ctx, e, "vx_world_batch_create", __FILE__, __LINE__);
+    if (rc != VX_OK) {
+        vx_mesh_batch_release(ctx, b);
+        return rc;
+    }
+    b->owns_world = true;
+    b->has_neighbors = true;
+    b->has_flags = true;
+    b->host_neighbors.assign(n * 6, -1);
+    b->total_quads = 0;
+    b->n_meshes = 0;
+    *out = b;
+    return VX_OK;
+}
+
+static int world_check_slots(VxContext *ctx, const VxMeshBatch *b, const int32_t *slots, int32_t n, const char *who) {
+    if (!ctx || !b || n < 0 || (n > 0 && !slots)) return vx_fail(ctx, VX_ERR_INVALID, who);
+    if (!b->owns_world || !b->has_neighbors) return vx_fail(ctx, VX_ERR_INVALID, "not a world batch (vx_world_batch_create)");
+    for (int32_t i = 0; i < n; ++i)
+        if (slots[i] < 0 || slots[i] >= b->n_chunks) return vx_fail(ctx, VX_ERR_INVALID, "slot out of range");
+    return VX_OK;
+}
+
+int vx_world_batch_assign(VxContext *ctx, VxMeshBatch *b, const int32_t *slots, int32_t n, const int32_t *positions, const int32_t *neighbors) {
+    int rc = world_check_slots(ctx, b, slots, n, "vx_world_batch_assign: bad argument");
+    if (rc != VX_OK || n == 0) return rc;
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int32_t i = 0; i < n; ++i) {
+        const size_t s = (size_t)slots[i];
+        if (positions) VX_CUDA(ctx, cudaMemcpyAsync(b->positions.as<int32_t>() + 3 * s, positions + 3 * (size_t)i, 12, cudaMemcpyHostToDevice, ctx->stream));
+        if (neighbors) {
+            for (int f = 0; f < 6; ++f) {
+                const int32_t nb = neighbors[6 * (size_t)i + f];
+                if (nb >= b->n_chunks || nb < -3) return vx_fail(ctx, VX_ERR_INVALID, "vx_world_batch_assign: neighbour out of range");
+                b->host_neighbors[6 * s + f] = nb;
+            }
+            VX_CUDA(ctx, cudaMemcpyAsync(b->world_neighbors.as<int32_t>() + 6 * s, neighbors + 6 * (size_t)i, 24, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the caller's arrays may go away
+    return VX_OK;
+}
+
+int vx_world_batch_generate(VxContext *ctx, VxMeshBatch *b, const int32_t *slots, int32_t n, const int32_t *positions,
+                            const VxTerrainParams *params, uint8_t *uniform_flags_out) {
+    int rc = world_check_slots(ctx, b, slots, n, "vx_world_batch_generate: bad argument");
+    if (rc != VX_OK || n == 0) return rc;
+    if (!positions || !params) return vx_fail(ctx, VX_ERR_INVALID, "vx_world_batch_generate: bad argument");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nn = (size_t)n;
+    VX_CUDA(ctx, ctx->tmp_b.reserve(nn * VX_CHUNK_VOLUME + 16));
+    std::vector<uint8_t> flags(nn);
+    rc = vx_generate_terrain(ctx, positions, n, params, ctx->tmp_b.as<uint8_t>(), flags.data()); // Chunk::generate_terrain chunk.rs:114-207
+    if (rc != VX_OK) return rc;
+    for (size_t i = 0; i < nn; ++i) {
+        const size_t s = (size_t)slots[i];
+        VX_CUDA(ctx, cudaMemcpyAsync(b->world_voxels.as<uint8_t>() + s * VX_CHUNK_VOLUME, ctx->tmp_b.as<uint8_t>() + i * VX_CHUNK_VOLUME, VX_CHUNK_VOLUME,
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+        VX_CUDA(ctx, cudaMemsetAsync(b->world_flags.as<uint8_t>() + s, flags[i], 1, ctx->stream));
+        VX_CUDA(ctx, cudaMemcpyAsync(b->positions.as<int32_t>() + 3 * s, positions + 3 * i, 12, cudaMemcpyHostToDevice, ctx->stream));
+        if (uniform_flags_out) uniform_flags_out[i] = flags[i];
+    }
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+int vx_world_batch_unload(VxContext *ctx, VxMeshBatch *b, const int32_t *slots, int32_t n) {
+    int rc = world_check_slots(ctx, b, slots, n, "vx_world_batch_unload: bad argument");
+    if (rc != VX_OK || n == 0) return rc;
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int32_t i = 0; i < n; ++i) { // an absent chunk: "uniform air" for any stale neighbour reference, no mesh, no neighbours of its own
+        const size_t s = (size_t)slots[i];
+        VX_CUDA(ctx, cudaMemsetAsync(b->world_flags.as<uint8_t>() + s, 1, 1, ctx->stream));
+        VX_CUDA(ctx, cudaMemsetAsync(b->has_mesh.as<uint8_t>() + s, 0, 1, ctx->stream));
+        VX_CUDA(ctx, cudaMemsetAsync(b->quad_count.as<uint32_t>() + s, 0, 4, ctx->stream));
+        VX_CUDA(ctx, cudaMemsetAsync(b->world_neighbors.as<int32_t>() + 6 * s, 0xFF, 24, ctx->stream));
+        for (int f = 0; f < 6; ++f) b->host_neighbors[6 * s + f] = -1;
+    }
+    b->n_meshes = -1;
+    return VX_OK;
+}
+
+int vx_world_batch_remesh(VxContext *ctx, VxMeshBatch *b, const int32_t *slots, int32_t n) {
+    int rc = world_check_slots(ctx, b, slots, n, "vx_world_batch_remesh: bad argument");
+    if (rc != VX_OK || n == 0) return rc;
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<int32_t> list;
+    std::vector<uint8_t> seen((size_t)b->n_chunks, 0);
+    for (int32_t i = 0; i < n; ++i)
+        if (!seen[slots[i]]) { seen[slots[i]] = 1; list.push_back(slots[i]); }
+    return remesh_listed(ctx, b, list);
 }
 
 } // extern "C"

@@ -174,6 +174,29 @@ typedef struct {
 VX_API int vx_generate_terrain(VxContext *ctx, const int32_t *positions, int32_t n, const VxTerrainParams *params, uint8_t *d_voxels_out,
                         uint8_t *uniform_flags_out);
 
+/* ---- streaming world: World::update (world.rs:57-100) and the mesh cache of the frame loop
+ * (main.rs:225-280) with the voxels resident on the device.  A world batch has `capacity` chunk slots; the host
+ * (differential_projection_voxel_renderer_b200/world.py mirrors `World`) decides which lattice position lives in
+ * which slot, the device holds voxels, Uniform flags, neighbour table and meshes.  A slot without a chunk is
+ * "uniform air without neighbours": it has no mesh and is an absent neighbour (faces towards it are exposed,
+ * binary_greedy.rs:127-168 with a missing map entry). ---- */
+VX_API int vx_world_batch_create(VxContext *ctx, int32_t capacity, VxMeshBatch **out);
+/* positions (n x 3, may be NULL) and neighbour rows (n x 6: slot of the chunk in direction +X,-X,+Y,-Y,+Z,-Z or
+ * VX_NBR_NONE; may be NULL) of the listed slots. */
+VX_API int vx_world_batch_assign(VxContext *ctx, VxMeshBatch *b, const int32_t *slots, int32_t n, const int32_t *positions,
+                          const int32_t *neighbors);
+/* Chunk::generate_terrain (chunk.rs:114-207, as vx_generate_terrain) for n new chunks straight into their slots:
+ * voxels, Uniform flag and position.  uniform_flags_out (n bytes, may be NULL) returns 0 / 1 + block type. */
+VX_API int vx_world_batch_generate(VxContext *ctx, VxMeshBatch *b, const int32_t *slots, int32_t n, const int32_t *positions,
+                            const VxTerrainParams *params, uint8_t *uniform_flags_out);
+/* chunks.retain(..) / mesh_cache.retain(..) (world.rs:92-97, main.rs:275): the slots become empty. */
+VX_API int vx_world_batch_unload(VxContext *ctx, VxMeshBatch *b, const int32_t *slots, int32_t n);
+/* mesh_chunk_in_indexed_world (binary_greedy.rs:127) for exactly the listed slots (main.rs:255-272); every other
+ * mesh stays as it is, even if its neighbourhood changed since it was built -- the reference's cache is stale in
+ * the same way.  Quads are appended to the stream; when it is full the live quads are compacted (copied, not
+ * re-meshed). */
+VX_API int vx_world_batch_remesh(VxContext *ctx, VxMeshBatch *b, const int32_t *slots, int32_t n);
+
 /* ---- meshing ---------------------------------------------------------- */
 
 /* BinaryGreedyMesher::mesh_world (binary_greedy.rs:62-78) / mesh_chunk_in_world (:83) /
