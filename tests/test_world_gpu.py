@@ -70,7 +70,7 @@ def test_streaming_world_on_device_matches_the_reference_loop(ctx, ob, vd, cap):
         # the frame: oracle renderer over the reference's cache, same list order
         allp, omb = _oracle_batch(ob, ref)
         oidx = {p: i for i, p in enumerate(allp)}
-        oids = np.array([oidx[p] for p in sorted(vis_ref) if p in ref.mesh_cache], dtype=np.int32)
+        oids = np.array([oidx[p] for p in sorted(vis_ref) if ref.mesh_cache.get(p) is not None], dtype=np.int32)  # Some(Some(mesh)), main.rs:281
         oc, od, osurv = ob.render_frame(omb, oids, vp, cam.position, ocfg, atlas)
         assert [allp[i] for i in osurv.tolist()] == [next(p for p, s in w.chunks.items() if s == sl) for sl in surv.tolist()]
         assert np.array_equal(depth.view(np.uint32), od.view(np.uint32)) and np.array_equal(color, oc), f"step {step}: frame differs"
