@@ -113,6 +113,7 @@ PROTOTYPES = {
     "vx_span_walk_quads": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "vx_span_walk_quads_device": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "vx_fill_spans": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "vx_hyper_pipeline_render": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _P, _P, C.POINTER(_I)]),
     "vx_render_frame_device": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig)]),
     "vx_render_frame_into": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig), _P, _P]),
     "vx_framebuffer_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I), C.POINTER(_I)]),

@@ -509,6 +509,19 @@ def render_frame(batch: MeshBatch, view_proj, camera_position, cfg: VxFrameConfi
     return color_out, depth_out, (surv[:ns.value] if survivors_out is not None else surv[:ns.value].copy())
 
 
+def hyper_pipeline_render(batch: MeshBatch, mesh_ids, view_proj, framebuffer: Framebuffer, ctx: Optional[Context] = None) -> int:
+    """The Hyper-Pipeline for a list of meshes (vx_hyper_pipeline_render): face packets -> PacketPipeline
+    (packet_pipeline.rs:69-142) -> span walker, into `framebuffer` (read-modify-write).  Returns the quads that passed the
+    packet backface test and the frustum mask."""
+    ctx = ctx or batch.ctx
+    vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+    ids = np.ascontiguousarray(mesh_ids, dtype=np.int32).ravel()
+    n = C.c_int32(0)
+    ctx.check(ctx.lib.vx_hyper_pipeline_render(ctx.handle, batch.handle, _p(ids), int(ids.size), _p(vp), framebuffer.width, framebuffer.height,
+                                               _p(framebuffer.color_buffer), _p(framebuffer.depth_buffer), C.byref(n)))
+    return int(n.value)
+
+
 def render_frame_macrotile(batch: MeshBatch, mesh_ids, view_proj, cfg: VxFrameConfig, want_tile_depth: bool = True,
                            ctx: Optional[Context] = None):
     """render_frame_macrotile (macrotile_renderer.rs:51-170).  Returns (color (H,W) u32, tile depth (H,W) f32 or None --

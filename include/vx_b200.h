@@ -348,6 +348,18 @@ VX_API int vx_span_walk_quads_device(VxContext *ctx, const float *d_boxes, const
 VX_API int vx_fill_spans(VxContext *ctx, const int32_t *y, const int32_t *x_start, const int32_t *x_end, const float *depth,
                   const uint32_t *color, int32_t n, int32_t width, int32_t height, uint32_t *color_inout, float *depth_inout);
 
+/* The Hyper-Pipeline (tests/span_walker_fuzz_tests.rs:158-173, benches/differential_projection.rs) for a
+ * list of meshes of a batch, device-resident end to end: ChunkFacePackets::from_chunk_mesh (face_packets.rs:122-174:
+ * packets of 32 consecutive quads per face) -> PacketPipeline::process_chunk_packets (packet_pipeline.rs:69-142: one
+ * FaceBasis per packet from the packet's first quad, packet-level backface test normal.z < 0, scalar projection
+ * project_single_scalar with exact division, frustum mask :279-293) -> SpanWalkerRasterizer::rasterize_projected_packet
+ * per packet, all in mesh-list order.  W x H host framebuffer, read-modify-write.  *n_visible_quads (may be NULL) =
+ * quads that passed the backface and frustum tests.  The reference's AVX2 projection (reciprocal + Newton step) is not
+ * reproduced; this is its scalar path. */
+VX_API int vx_hyper_pipeline_render(VxContext *ctx, const VxMeshBatch *batch, const int32_t *mesh_ids, int32_t n_meshes,
+                             const float vp[16], int32_t width, int32_t height, uint32_t *color_inout, float *depth_inout,
+                             int32_t *n_visible_quads);
+
 /* Rasterizer::render_mesh / render_mesh_into_slice / render_mesh_into_tile (rasterizer.rs:385-431)
  * for one mesh into a caller framebuffer (W x H host arrays, read-modify-write: depth-tested against
  * the existing contents).  rect = PixelTarget::rect() = (x0, y0, w, h). */

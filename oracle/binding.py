@@ -345,3 +345,42 @@ def render_frame_macrotile(mb: MeshBatch, mesh_ids, vp, cfg: FrameConfig, atlas:
     if want_kinds:
         return color, depth, proj[:k].copy(), kind[:k].copy()
     return color, depth, proj[:k].copy()
+
+
+def hyper_pipeline_render(mb: MeshBatch, mesh_ids, vp, color, depth):
+    """The reference's Hyper-Pipeline for a list of meshes, composed from the restated pieces exactly as
+    tests/span_walker_fuzz_tests.rs:158-173 / benches/differential_projection.rs do: ChunkFacePackets::from_chunk_mesh
+    (face_packets.rs:122-174) -> PacketPipeline::process_chunk_packets (packet_pipeline.rs:69-142: one FaceBasis per
+    packet taken from the packet's FIRST quad, packet-level backface test normal.z < 0, scalar projection,
+    frustum mask :279-293) -> SpanWalkerRasterizer::rasterize_projected_packet per surviving packet.
+    Returns (packets drawn, quads visible)."""
+    vp = np.ascontiguousarray(vp, dtype=np.float32).reshape(16)
+    h, w = color.shape
+    n_packets = n_quads = 0
+    for mid in np.asarray(mesh_ids, dtype=np.int64).tolist():
+        if not mb.has_mesh[mid]:
+            continue
+        faces = face_packets(mb, mid)
+        for f in range(6):
+            for pk in faces[f]:
+                n = int(pk["len"])
+                if n == 0:
+                    continue
+                basis = face_basis(f, mb.positions[mid], int(pk["axis_pos"][0]), vp)
+                if not (basis[3, 2] < np.float32(0.0)):  # is_front_facing differential_projection.rs:78-82
+                    continue
+                x0, y0, x1, y1, z = project_packet(basis, pk["u_min"][:n], pk["v_min"][:n], pk["u_len"][:n], pk["v_len"][:n])
+                one, zero = np.float32(1.0), np.float32(0.0)
+                vis = (x1 >= -one) & (x0 <= one) & (y1 >= -one) & (y0 <= one) & (z >= zero) & (z <= one)  # test_aabb_inside
+                if not vis.any():
+                    continue
+                mask = 0
+                for i in range(n):
+                    if vis[i]:
+                        mask |= 1 << i
+                bt = np.ascontiguousarray(pk["block_type"][:n])
+                lib().vxo_span_walk_packet(_p(x0), _p(y0), _p(x1), _p(y1), _p(z), _p(bt), C.c_uint32(mask), C.c_int32(n),
+                                           C.c_int32(w), C.c_int32(h), _p(color), _p(depth))
+                n_packets += 1
+                n_quads += int(vis.sum())
+    return n_packets, n_quads

@@ -156,3 +156,52 @@ def test_span_walker_device_entry_matches_the_host_entry(ctx, ob):
     # n == 0 and bad arguments
     ctx.check(ctx.lib.vx_span_walk_quads_device(ctx.handle, None, None, 0, w, h, C.c_void_p(col.data_ptr()), C.c_void_p(dep.data_ptr())))
     assert ctx.lib.vx_span_walk_quads_device(ctx.handle, None, None, 5, w, h, C.c_void_p(col.data_ptr()), C.c_void_p(dep.data_ptr())) != 0
+
+
+# ---- the Hyper-Pipeline end to end on the device -------------------------------------------------------------
+def test_hyper_pipeline_reference_bench_scene(ctx, ob):
+    """benches/differential_projection.rs:8-36: the y < 8 + ((x + z) % 4) Stone chunk under
+    persp(70 deg, 16/9, 0.1, 1000) * look_at((64,50,100) -> (64,32,64)), 1280 x 720: face packets -> packet pipeline -> span
+    walker on the device equals the composition of the restated pieces, bit for bit."""
+    import vx_kat as kat
+    from differential_projection_voxel_renderer_b200 import camera
+    vox = kat.chunk_slab().reshape(1, -1)
+    batch = api.BinaryGreedyMesher.mesh_batch(vox, [(0, 0, 0)], None, None, ctx)
+    ref = ob.mesh_chunks(vox)
+    w, h = 1280, 720
+    proj = camera.perspective_rh(np.radians(np.float32(70.0)), 16 / 9, 0.1, 1000.0)
+    vp = camera.mat4_mul(proj, camera.look_at_rh((64.0, 50.0, 100.0), (64.0, 32.0, 64.0), (0.0, 1.0, 0.0))).reshape(16)
+    c, d = _blank(w, h)
+    n_packets, n_quads = ob.hyper_pipeline_render(ref, [0], vp, c, d)
+    fb = api.Framebuffer(w, h)
+    got = api.hyper_pipeline_render(batch, [0], vp, fb, ctx)
+    assert got == n_quads and n_quads > 0
+    assert _same(fb, c, d) and int((c != 0).sum()) > 1000
+    batch.release()
+
+
+@pytest.mark.parametrize("cam_i", [0, 1, 3, 5])
+def test_hyper_pipeline_terrain_world_bit_exact(ctx, ob, cam_i):
+    import vx_scenes
+    pos, world, p, v, nb = vx_scenes.terrain_scene(5)
+    batch = api.BinaryGreedyMesher.mesh_batch(v, p, nb, None, ctx)
+    ref = ob.mesh_chunks(v, nb, None, p)
+    w, h = 640, 360
+    vp = vx_scenes.path_camera(cam_i, w, h).view_projection()
+    ids = np.flatnonzero(ref.has_mesh != 0).astype(np.int32)
+    if cam_i == 1:   # list order is the caller's, duplicates and meshless chunks allowed
+        ids = np.concatenate([ids[::-1], ids[:5], np.flatnonzero(ref.has_mesh == 0)[:3].astype(np.int32)])
+    c, d = _blank(w, h)
+    if cam_i == 3:   # existing contents take part in the depth test
+        d[100:200, 100:400] = 0.2
+        c[100:200, 100:400] = 0xFF445566
+    fb = api.Framebuffer(w, h)
+    fb.color_buffer[...] = c; fb.depth_buffer[...] = d
+    n_packets, n_quads = ob.hyper_pipeline_render(ref, ids, vp, c, d)
+    got = api.hyper_pipeline_render(batch, ids, vp, fb, ctx)
+    assert got == n_quads
+    assert _same(fb, c, d)
+    assert api.hyper_pipeline_render(batch, np.zeros(0, dtype=np.int32), vp, fb, ctx) == 0 and _same(fb, c, d)
+    with pytest.raises(api.VxError):
+        api.hyper_pipeline_render(batch, [10**6], vp, fb, ctx)
+    batch.release()
