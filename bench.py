@@ -662,7 +662,23 @@ def run_cuda(args):
                 t0 = time.perf_counter()
                 api.render_frame(batch, vp, cam.position, cfg_m, mesh_ids=ids18, want_depth=False, color_out=loop.color, ctx=ctx)
                 mt_ms.append((time.perf_counter() - t0) * 1e3)
-            a18 = {"span_walker_full_packet_32_quads_1920x1080_ms": float(np.median(sw_ms)), "span_walker_cpu_port_ms": sw_cpu_ms,
+            # Hyper-Pipeline (benches/differential_projection.rs:8-36 scene; host framebuffers in and out, wall clock)
+            import vx_kat
+            hb = api.BinaryGreedyMesher.mesh_batch(vx_kat.chunk_slab().reshape(1, -1), [(0, 0, 0)], None, None, ctx)
+            from differential_projection_voxel_renderer_b200 import camera as _cam
+            hvp = _cam.mat4_mul(_cam.perspective_rh(np.radians(np.float32(70.0)), 16 / 9, 0.1, 1000.0),
+                                _cam.look_at_rh((64.0, 50.0, 100.0), (64.0, 32.0, 64.0), (0.0, 1.0, 0.0))).reshape(16)
+            hfb = api.Framebuffer(1280, 720)
+            hyper_quads = api.hyper_pipeline_render(hb, [0], hvp, hfb, ctx)
+            hp_ms = []
+            for _ in range(5):
+                hfb = api.Framebuffer(1280, 720)
+                t0 = time.perf_counter()
+                api.hyper_pipeline_render(hb, [0], hvp, hfb, ctx)
+                hp_ms.append((time.perf_counter() - t0) * 1e3)
+            hb.release()
+            a18 = {"hyper_pipeline_1280x720_one_chunk_ms": float(np.median(hp_ms)), "hyper_pipeline_visible_quads": hyper_quads,
+                   "span_walker_full_packet_32_quads_1920x1080_ms": float(np.median(sw_ms)), "span_walker_cpu_port_ms": sw_cpu_ms,
                    "span_walker_matches_oracle": same18, "span_walker_launches": 5,
                    "macrotile_frame_1280x720_vd12_e2e_ms": float(np.median(mt_ms)), "macrotile_meshes": int(ids18.size),
                    "note": "vx_span_walk_quads_device (benches/span_walker.rs:36-77 workload, framebuffer resident) and vx_render_frame with cfg.macrotile = 1 (render_frame_macrotile) through the host API into mapped host memory, wall clock"}
