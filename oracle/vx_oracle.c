@@ -846,7 +846,7 @@ static void *stripe_worker(void *arg) {
         int y0 = s * j->stripe_h; /* split_into_stripes framebuffer.rs:392-431 */
         if (y0 >= H) continue;
         int rows = imin(H - y0, j->stripe_h);
-        target_t tg = {W, H, 0, y0, W, rows, j->color, j->depth, j->cfg, j->atlas};
+        target_t tg = {W, H, 0, y0, W, rows, j->color, j->depth, j->cfg, j->atlas, 0};
         for (int32_t si = 0; si < j->n_proj; ++si) {
             int32_t pj = j->ord2[si];
             int start = imin(j->rect_y[2 * pj] / j->stripe_h, j->stripe_count - 1);
@@ -1273,7 +1273,7 @@ int vxo_render_frame_macrotile(const vxo_mesh_batch *mb, const int32_t *mesh_ids
         for (int ty = 0; ty < tiles_y; ++ty)
             for (int tx = 0; tx < tiles_x; ++tx) {
                 const int x0 = tx * 128, y0 = ty * 128;
-                target_t tg = {W, H, x0, y0, imin(x0 + 128, W) - x0, imin(y0 + 128, H) - y0, color, depth, cfg, atlas};
+                target_t tg = {W, H, x0, y0, imin(x0 + 128, W) - x0, imin(y0 + 128, H) - y0, color, depth, cfg, atlas, 0};
                 for (int32_t j = 0; j < n_proj; ++j) /* bins.get_bin(tx, ty), push order = list order */
                     if (kind[j] == 1 && tx >= tiles[4 * j] && tx <= tiles[4 * j + 2] && ty >= tiles[4 * j + 1] && ty <= tiles[4 * j + 3])
                         render_mesh_tiny_quads(mb, proj[j], vp, &tg);
