@@ -74,3 +74,19 @@ def test_cuda_reproduces_golden(ctx):
         assert sha(c) == e["color_sha"] and sha(d) == e["depth_sha"]
         assert int((c != 0xFF87CEEB).sum()) == e["covered"]
     batch.release()
+
+
+def test_oracle_reproduces_golden_v2(ob):
+    """Regression fixtures of the later restatements (macrotile renderer, occlusion pass, barycentric mesh path, span
+    walker, Hyper-Pipeline composition): tests/golden/golden_v2.json, generator tests/golden/make_golden_v2.py."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_v2", os.path.join(here, "make_golden_v2.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.load(open(os.path.join(here, "golden_v2.json")))
+    got = mod.build()
+    assert got == want
+    assert all(e["barycentric"]["covered"] > 0 for e in want["frames"].values()) and want["span_walker"]["covered"] > 0
