@@ -8,7 +8,8 @@
 // visited, never the order of two fragments of one pixel.  Here every fragment is a 64-bit key
 //   [ order-preserving depth : 32 | 1 + submission index : 32 ]
 // merged with atomicMin; the pixel's previous content enters as [depth | 0], which wins every tie exactly like
-// `depth < stored` loses it.  Four launches: setup (screen boxes + work count per quad), scan, fill, resolve.
+// `depth < stored` loses it.  Five launches: key init, setup (screen boxes + work count per quad), scan, fill, resolve.
+// vx_hyper_pipeline_render swaps the setup for the Hyper-Pipeline front end (face packets -> PacketPipeline, one thread per quad).
 #include "vx_common.cuh"
 #include "vx_math.cuh"
 #include "vx_scan.cuh"
