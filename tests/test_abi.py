@@ -73,3 +73,27 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "vx_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/vx_b200.h is the drop-in boundary: it must compile as C99 (no C++ in the signatures) and a C program
+    must link against libvx_b200.so and find the host-only helpers."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "vx_b200.h"\n'
+        "int main(void) {\n"
+        "    VxFrameConfig cfg;\n"
+        "    vx_default_frame_config(&cfg, 1280, 720);\n"
+        "    VxAtlas atlas;\n"
+        "    vx_default_atlas(&atlas);\n"
+        '    printf("%d %d %d %d %u %zu %zu\\n", cfg.width, cfg.height, cfg.occlusion_grid_w, cfg.occlusion_grid_h, atlas.palette[1][0],\n'
+        "           sizeof(VxFrameConfig), sizeof(VxFacePacket32));\n"
+        "    return 0;\n}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "differential_projection_voxel_renderer_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lvx_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["1280", "720", "128", "72", str(0xFF007D00), "80", "224"]
