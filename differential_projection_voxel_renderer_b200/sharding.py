@@ -33,6 +33,39 @@ def stripe_of(height: int, rank: int, world: int) -> Tuple[int, int]:
     return y0, min(per, height - y0)
 
 
+def balanced_stripes(band_cost, height: int, world: int, band: int = 8, row_cost: float = 0.0) -> List[Tuple[int, int]]:
+    """Contiguous stripes of roughly equal WORK instead of equal height: [(y0, rows)] per rank, covering rows
+    0 .. height without gaps, boundaries on multiples of `band` rows.  band_cost[b] is the measured work of rows
+    [b * band, (b + 1) * band) (e.g. the triangles binned into that tile row, vx_frame_bin_counts summed over x);
+    row_cost is added per row for the clear / write-out every row costs.  Rows are independent in the span
+    rasterizer (rasterizer.rs:1401-1427), so any contiguous split renders the same frame as split_into_stripes; this
+    one keeps the horizon band from landing on a single GPU.  Greedy prefix split: stripe r ends at the first band
+    where the running cost reaches (r + 1) / world of the total; a rank may get no rows when world exceeds the bands."""
+    if world <= 0:
+        raise ValueError("world must be positive")
+    n_bands = (height + band - 1) // band
+    cost = np.asarray(band_cost, dtype=np.float64).ravel()
+    if cost.size != n_bands:
+        raise ValueError(f"band_cost has {cost.size} entries, expected {n_bands}")
+    rows_in = np.minimum(band, height - band * np.arange(n_bands)).astype(np.float64)
+    cum = np.cumsum(np.maximum(cost, 0.0) + row_cost * rows_in)
+    total = float(cum[-1]) if n_bands else 0.0
+    cuts = [0]
+    for r in range(1, world):
+        if total <= 0.0:
+            b = min(n_bands, (n_bands * r + world - 1) // world)  # no information: equal bands
+        else:
+            b = int(np.searchsorted(cum, total * r / world, side="left")) + 1
+        cuts.append(min(max(b, cuts[-1]), n_bands))
+    cuts.append(n_bands)
+    out = []
+    for r in range(world):
+        y0 = min(cuts[r] * band, height)
+        y1 = min(cuts[r + 1] * band, height)
+        out.append((y0, y1 - y0))
+    return out
+
+
 def merge_mesh_shards(shards: Sequence[Dict[str, np.ndarray]], n_chunks: int, world: Optional[int] = None) -> Dict[str, np.ndarray]:
     """Put per-rank mesh shards (dicts as MeshBatch.download(): quads (Q,3), quad_count, slice_offsets (n,6,33),
     face_aabb (n,6,6), has_mesh; shard r holds the chunks chunk_shard(n_chunks, r, world) in that order) back into

@@ -110,3 +110,31 @@ def test_chunk_shards_partition_the_batch():
         for world in (1, 2, 4, 8):
             ids = np.concatenate([sharding.chunk_shard(n, r, world) for r in range(world)])
             assert np.array_equal(np.sort(ids), np.arange(n))
+
+
+def test_balanced_stripes_cover_the_frame_and_even_out_the_work():
+    """sharding.balanced_stripes: contiguous, gap-free, band-aligned; the heaviest stripe is far lighter than with the
+    equal-height split when the work sits in a horizon band (the headline camera: 354 vs ~27,500 triangles at N = 2)."""
+    from differential_projection_voxel_renderer_b200 import sharding
+    h, band = 720, 8
+    n_bands = h // band
+    cost = np.zeros(n_bands)
+    cost[44:52] = 3000.0   # the horizon band just below mid-screen
+    cost[52:] = 40.0       # near terrain
+    for world in (1, 2, 3, 4, 8):
+        st = sharding.balanced_stripes(cost, h, world, band, row_cost=1.0)
+        assert len(st) == world and st[0][0] == 0 and sum(r for _, r in st) == h
+        for (y0, r), (y1, _) in zip(st, st[1:]):
+            assert y0 + r == y1 and y0 % band == 0
+        work = [cost[y0 // band:(y0 + r + band - 1) // band].sum() + r for y0, r in st]
+        eq = [sharding.stripe_of(h, k, world) for k in range(world)]
+        eq_work = [cost[y0 // band:(y0 + r + band - 1) // band].sum() + r for y0, r in eq]
+        assert max(work) <= max(eq_work) + 1e-9
+        if world in (2, 4):
+            assert max(work) < 0.75 * max(eq_work)
+    # degenerate inputs: no cost information -> equal bands; more ranks than bands -> empty stripes at the end
+    assert sharding.balanced_stripes(np.zeros(4), 32, 2) == [(0, 16), (16, 16)]
+    st = sharding.balanced_stripes(np.ones(2), 13, 4)
+    assert sum(r for _, r in st) == 13 and [y for y, _ in st] == sorted(y for y, _ in st)
+    with pytest.raises(ValueError):
+        sharding.balanced_stripes(np.ones(3), 32, 2)
