@@ -111,17 +111,21 @@ def all_gather_mesh_shards(local: Dict[str, np.ndarray], n_chunks: int, group=No
     return merge_mesh_shards(shards, n_chunks, world)  # type: ignore[arg-type]
 
 
-def gather_stripes(stripe, height: int, width: int, dst: int = 0, group=None):
+def gather_stripes(stripe, height: int, width: int, dst: int = 0, group=None, stripes: Optional[Sequence[Tuple[int, int]]] = None):
     """Gather the ranks' disjoint stripes (torch tensors (rows_r, width), any device the backend supports) to `dst`
-    and return the composed (height, width) frame there (None elsewhere).  Stripes are padded to the common
-    ceil(height / world) rows for the collective."""
+    and return the composed (height, width) frame there (None elsewhere).  `stripes` = [(y0, rows)] per rank
+    (e.g. balanced_stripes); default: the equal split of stripe_of.  Stripes are padded to the tallest one for the
+    collective."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    per = (height + world - 1) // world
-    y0, rows = stripe_of(height, rank, world)
+    layout = [stripe_of(height, r, world) for r in range(world)] if stripes is None else [(int(y), int(r)) for y, r in stripes]
+    if len(layout) != world:
+        raise ValueError(f"{len(layout)} stripes for {world} ranks")
+    per = max(1, max(r for _, r in layout))
+    y0, rows = layout[rank]
     if stripe.shape[0] != rows or stripe.shape[1] != width:
         raise ValueError(f"rank {rank}: stripe is {tuple(stripe.shape)}, expected ({rows}, {width})")
     padded = torch.zeros((per, width), dtype=stripe.dtype, device=stripe.device)
@@ -132,7 +136,7 @@ def gather_stripes(stripe, height: int, width: int, dst: int = 0, group=None):
         return None
     frame = torch.empty((height, width), dtype=stripe.dtype, device=stripe.device)
     for r in range(world):
-        ry0, rr = stripe_of(height, r, world)
+        ry0, rr = layout[r]
         if rr:
             frame[ry0:ry0 + rr] = bufs[r][:rr]
     return frame

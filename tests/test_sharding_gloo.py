@@ -75,6 +75,21 @@ def _worker(rank, world, port, w, h, out_dir):
             assert int((fc != cfg.clear_color).sum()) > 500
         else:
             assert frame is None
+        # the same frame from work-balanced stripes: band costs = covered pixels per 8-row band of the full frame (every
+        # rank derives the identical split from the identical calibration frame, no communication)
+        nb8 = (h + 7) // 8
+        band_cost = np.array([(fc[b * 8:(b + 1) * 8] != cfg.clear_color).sum() for b in range(nb8)], dtype=np.float64)
+        layout = sharding.balanced_stripes(band_cost, h, world, 8, row_cost=1.0)
+        by0, brows = layout[rank]
+        color = np.full((h, w), cfg.clear_color, dtype=np.uint32)
+        depth = np.full((h, w), np.inf, dtype=np.float32)
+        if brows:
+            for m in order.tolist():
+                ob.render_mesh(full, int(m), vp, cfg, atlas, (0, by0, w, brows), color, depth)
+        frame = sharding.gather_stripes(torch.from_numpy(color[by0:by0 + brows].view(np.int32).copy()), h, w, dst=0, stripes=layout)
+        if rank == 0:
+            assert np.array_equal(frame.numpy().view(np.uint32), fc)
+            assert layout != [sharding.stripe_of(h, r, world) for r in range(world)] or band_cost.std() == 0
         dist.barrier()
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
