@@ -273,16 +273,18 @@ VX_API void vx_default_atlas(VxAtlas *atlas); /* TextureAtlas::default texture.r
 /* Rasterizer::new_with_atlas (rasterizer.rs:357): atlas used by later render calls. */
 VX_API int vx_set_atlas(VxContext *ctx, const VxAtlas *atlas);
 
-/* main.rs RedrawRequested steady state (:283-297, :368-377) + render_frame (:379-608), occlusion off:
+/* main.rs RedrawRequested steady state (:283-297, :368-377) + render_frame (:379-608):
  * VisibleMesh list -> distance sort -> AABB projection / reject (filter B) -> near-depth sort ->
- * project + clip + backface-cull every quad -> stripe-binned span rasterization -> framebuffer.
+ * [occlusion pass :501-526 when cfg->occlusion_culling] -> project + clip + backface-cull every quad ->
+ * stripe-binned span rasterization -> framebuffer.  cfg->macrotile selects render_frame_macrotile's order instead.
  *   mesh_ids      chunks of `batch` that passed filter A (caller order = tie-break order), or NULL
  *                 with n_meshes < 0 to run filter A on the device over the batch's own positions
  *                 (view_distance then required)
  *   color_out     rows x width u32 ARGB (may be NULL), depth_out rows x width f32 (may be NULL),
  *                 rows = stripe_rows or height.  Device-mapped page-locked buffers (vx_host_alloc) are written in
  *                 place by the kernel; other host memory is filled by a copy from the device framebuffer
- *   survivors_out draw order (capacity n_meshes / n_chunks; entries past *n_survivors are undefined), may be NULL */
+ *   survivors_out draw order (capacity n_meshes / n_chunks; entries past *n_survivors are undefined), may be NULL;
+ *                 meshes dropped by filter B or by the occlusion pass are not in it */
 VX_API int vx_render_frame(VxContext *ctx, const VxMeshBatch *batch, const int32_t *mesh_ids, int32_t n_meshes,
                     const float vp[16], const float cam_pos[3], int32_t view_distance, const VxFrameConfig *cfg,
                     uint32_t *color_out, float *depth_out, int32_t *survivors_out, int32_t *n_survivors);
