@@ -116,26 +116,45 @@ class ClockSampler:
 
 
 def build_scene():
+    """The seeded world of BASELINE configs[2]: every lattice chunk within VD of chunk (0,0,0) (7,153 of them, Uniform
+    ones included -- the reference's get_visible_chunks_frustum walks all loaded chunks, world.rs:118-146), camera of
+    main.rs:51."""
     import vx_scenes
     pos, world, p, v, nb = vx_scenes.terrain_scene(VD)
     cam = vx_scenes.main_camera(W, H)
-    return pos, world, p, v, nb, cam
+    return {"pos": pos, "world": world, "p": p, "v": v, "nb": nb, "cam": cam,
+            "flags": world.uniform_flags, "nb_full": world.neighbor_table(), "v_full": world.voxels}
+
+
+def workload_config(n_gpus: int, sc, total_quads: int):
+    """`config` of the JSON line -- one function for both arms, so the driver sees the same dict."""
+    return {
+        "workload": "full frame 1280x720 view distance 12: filter A over every loaded chunk + filter B / draw order + project / near-clip / "
+                    "backface-cull every quad + span raster with depth buffer and textured shading; meshes cached (main.rs:225-280); "
+                    "BASELINE.json configs[2]",
+        "resolution": [W, H], "view_distance": VD,
+        "chunks": int(sc["pos"].shape[0]), "varied_chunks": int(sc["p"].shape[0]), "total_quads": int(total_quads),
+        "camera": "(0,10,20) yaw 0 pitch 0 fov 70",
+        "l2": "CUDA arm: L2 flushed between timed frames (256 MiB device write outside the timed events); CPU arm: not applicable",
+        "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} GPUs: work-balanced screen stripes, each rank's raster kernel stores its rows into the "
+                                                   "composed frame in GPU0's memory over NVLink (CUDA IPC peer mapping, no collective)",
+    }
 
 
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU implementation of the path (C restatement, see oracle/vx_oracle.h), all host threads
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_frame_baseline(p, v, nb, cam, min_seconds: float, threads: int, steps=None, warmup=1):
+def cpu_frame_baseline(sc, min_seconds: float, threads: int, steps=None, warmup=1):
     from oracle import binding as ob
-    ref = ob.mesh_chunks(v, nb, None, p)
+    pos, cam = sc["pos"], sc["cam"]
+    ref = ob.mesh_chunks(sc["v_full"], sc["nb_full"], sc["flags"], pos)
     vp = cam.view_projection()
-    vis = ob.cull_chunks(p, vp, cam.position, VD)
     cfg = ob.default_frame_config(W, H, n_threads=threads)
     atlas = ob.default_atlas()
     has = ref.has_mesh != 0
 
     def one_frame():
-        vis = ob.cull_chunks(p, vp, cam.position, VD)           # filter A
+        vis = ob.cull_chunks(pos, vp, cam.position, VD)           # filter A over all loaded chunks (world.rs:118-146)
         ids = np.flatnonzero((vis != 0) & has).astype(np.int32)
         return ob.render_frame(ref, ids, vp, cam.position, cfg, atlas)  # filter B + sort + raster
 
@@ -151,7 +170,7 @@ def cpu_frame_baseline(p, v, nb, cam, min_seconds: float, threads: int, steps=No
                 break
         elif el >= min_seconds:
             break
-    return n / el, n, el
+    return n / el, n, el, int(ref.quads.size // 3)
 
 
 def cpu_mesh_baseline(v, nb, min_seconds: float):
@@ -166,23 +185,26 @@ def cpu_mesh_baseline(v, nb, min_seconds: float):
     return n / el, n, el
 
 
+def cargo_note():
+    import shutil
+    return "cargo found on this box but the crate's dependencies are not vendored (no network)" if shutil.which("cargo") else \
+        "no cargo/rustc on this box: the Rust crate cannot be built"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    pos, world, p, v, nb, cam = build_scene()
+    sc = build_scene()
     threads = os.cpu_count() or 1
-    fps, n, el = cpu_frame_baseline(p, v, nb, cam, 0.0, threads, steps=max(1, args.steps), warmup=max(1, args.warmup))
+    fps, n, el, tq = cpu_frame_baseline(sc, 0.0, threads, steps=max(1, args.steps), warmup=max(1, args.warmup))
     out = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
         "ms_per_step": 1000.0 * el / n, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": "full frame 1280x720 view distance 12 (filter A + filter B/sort + project/clip/cull + span raster), "
-                                                     "meshes cached; BASELINE.json configs[2]",
-                                         "chunks": int(pos.shape[0]), "varied_chunks": int(p.shape[0]),
-                                         "camera": "(0,10,20) yaw 0 pitch 0 fov 70", "parallelism": f"{threads} host threads (stripes)"},
+        "data": "synthetic", "config": workload_config(args.gpus, sc, tq),
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n} full frames; C restatement of the reference CPU path (oracle/), stripe-parallel over all host threads; "
-                                   "the Rust reference itself cannot be built in this image (no cargo/rustc)"},
+                         "sample": f"{n} full frames; C restatement of the reference CPU path (oracle/), stripe-parallel over all {threads} host threads; "
+                                   + cargo_note()},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit_json_line(out)
@@ -192,50 +214,64 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------------------------------
-def finish_distributed(dist):
-    """All ranks leave together: barrier, tear the process group down, and exit without running interpreter-exit
-    destructors (torch's NCCL watchdog otherwise races the CUDA context teardown and aborts the process)."""
-    try:
-        dist.barrier()
-        dist.destroy_process_group()
-    finally:
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+def event_pair(torch):
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
 def run_cuda(args):
     import torch
-    from differential_projection_voxel_renderer_b200 import api
+    from differential_projection_voxel_renderer_b200 import api, multigpu, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     dist = None
     if world_size > 1:
+        import datetime
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        import datetime
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=300))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    pos, world, p, v, nb, cam = build_scene()
+    sc = build_scene()
+    pos, p, v, nb, cam = sc["pos"], sc["p"], sc["v"], sc["nb"], sc["cam"]
     vp = cam.view_projection()
     ctx = api.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    n_lattice, n_varied = int(pos.shape[0]), int(p.shape[0])
+    extra = {}
 
-    # ---- inputs resident in HBM --------------------------------------------------------------------------------
-    d_vox = torch.from_numpy(v).to(dev)
-    d_nb = torch.from_numpy(nb).to(dev)
-    d_pos = torch.from_numpy(p).to(dev)
-    n_chunks = int(p.shape[0])
+    def barrier():
+        if dist is not None:
+            dist.barrier()
 
-    # chunk-sharded meshing (sorted chunk id modulo n_gpu); the frame needs every visible mesh on every raster GPU
-    h = C.c_void_p()
-    ctx.check(ctx.lib.vx_mesh_chunks_device(ctx.handle, C.c_void_p(d_vox.data_ptr()), C.c_void_p(d_pos.data_ptr()),
-                                            C.c_void_p(d_nb.data_ptr()), None, n_chunks, C.byref(h)))
-    batch = api.MeshBatch(ctx, h)
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- inputs resident in HBM: the whole lattice (Uniform chunks carry a flag and no voxel data that is ever read) ------
+    d_voxf = torch.from_numpy(sc["v_full"]).to(dev)
+    d_posf = torch.from_numpy(pos).to(dev)
+    d_nbf = torch.from_numpy(sc["nb_full"]).to(dev)
+    d_flf = torch.from_numpy(sc["flags"]).to(dev)
+
+    def mesh_full_locally():
+        hh = C.c_void_p()
+        ctx.check(ctx.lib.vx_mesh_chunks_device(ctx.handle, C.c_void_p(d_voxf.data_ptr()), C.c_void_p(d_posf.data_ptr()),
+                                                C.c_void_p(d_nbf.data_ptr()), C.c_void_p(d_flf.data_ptr()), n_lattice, C.byref(hh)))
+        return api.MeshBatch(ctx, hh)
+
+    exchange = None
+    if world_size == 1:
+        batch = mesh_full_locally()
+    else:
+        # chunk-sharded meshing (chunk id modulo N) + device exchange: the frame below is rendered from the ASSEMBLED batch
+        exchange = multigpu.MeshShardExchange(ctx, n_lattice, rank, world_size, dev)
+        batch = exchange.sweep(d_voxf.data_ptr(), d_posf.data_ptr(), d_nbf.data_ptr(), d_flf.data_ptr())
     info = batch.info()
     total_quads = int(info.total_quads)
 
@@ -245,44 +281,48 @@ def run_cuda(args):
         with torch.cuda.stream(stream):
             flush.fill_(1)
 
-    # stripe of this rank (framebuffer.rs:392-431: ceil(H / n) rows per stripe)
     cfg = api.default_frame_config(W, H)
-    rows_per = (H + world_size - 1) // world_size
-    if world_size > 1:
-        from differential_projection_voxel_renderer_b200.sharding import stripe_of
-        cfg.stripe_y0, cfg.stripe_rows = stripe_of(H, rank, world_size)  # framebuffer.rs:403-427
     cfg_async = api.VxFrameConfig.from_buffer_copy(cfg)
     cfg_async.async_submit = 1
 
-    gather_bufs = None
+    # ---- one synchronous full frame on every rank: sizes the scratch, gives the per-tile-row work for the stripe split ----
+    api.render_frame_device(batch, vp, cam.position, cfg, VD, ctx)
+    st_full = api.frame_stats(ctx)
+    comp = None
+    stripes = [(0, H)]
+    frame_no = 0
     if world_size > 1:
-        gather_bufs = [torch.empty((rows_per, W), dtype=torch.int32, device=dev) for _ in range(world_size)] if rank == 0 else None
-        my_stripe = torch.empty((rows_per, W), dtype=torch.int32, device=dev)
-
-    class _Cai:
-        def __init__(self, ptr, shape, typestr):
-            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+        band = api.frame_bin_counts(ctx).sum(axis=1).astype(np.float64)  # triangles binned per 8-row band of the full frame
+        holder = [sharding.balanced_stripes(band, H, world_size, band=8, row_cost=float(band.sum()) / (4.0 * H))] if rank == 0 else [None]
+        dist.broadcast_object_list(holder, src=0)
+        stripes = [tuple(x) for x in holder[0]]
+        comp = multigpu.StripeCompositor(ctx, W, H, rank, world_size, want_depth=True)
+        comp.set_stripes(stripes)
 
     def step_device():
-        if world_size == 1:
+        nonlocal frame_no
+        if comp is None:
             api.render_frame_device(batch, vp, cam.position, cfg_async, VD, ctx)
-        else:  # the raster kernel writes this rank's rows straight into the gather buffer
-            api.render_frame_into(batch, vp, cam.position, cfg_async, VD, my_stripe.data_ptr(), 0, ctx)
-            with torch.cuda.stream(stream):
-                dist.gather(my_stripe, gather_bufs, dst=0)  # composite: disjoint stripes into GPU0
+        else:
+            comp.render(batch, vp, cam.position, cfg, VD, frame_no)
+            if rank == 0:
+                comp.complete(frame_no)  # every stripe of this frame has landed in GPU0's memory
+                comp.release(frame_no)
+        frame_no += 1
 
-    # ---- warm-up + correctness guard ----------------------------------------------------------------------------
-    api.render_frame_device(batch, vp, cam.position, cfg, VD, ctx)  # one synchronous frame sizes the frame scratch
-    for _ in range(max(3, args.warmup)):
+    # ---- warm-up ---------------------------------------------------------------------------------------------------
+    Wm = max(3, args.warmup)
+    for _ in range(Wm):
         step_device()
     ctx.synchronize()
-    st = api.frame_stats(ctx)
-    launches_per_frame = st.n_kernel_launches
+    if comp is not None:
+        comp.check()
+    api.frame_stats(ctx)
+    launches_per_frame = None
 
     # ---- timed region: exactly K frames, CUDA events on the launching stream, L2 flushed between frames ---------
     sampler = ClockSampler(local_rank)
-    if dist is not None:
-        dist.barrier()
+    barrier()
     torch.cuda.synchronize()
     sampler.start()
     K = max(1, args.steps)
@@ -296,134 +336,173 @@ def run_cuda(args):
         ends[i].record(stream)
     torch.cuda.synchronize()
     l1 = ctx.launch_count
+    launches_per_frame = (l1 - l0) / K
+    if comp is not None:
+        comp.check()
     # keep the same load running until the sampler has seen >= 1.5 s of it (the timed frames are ~tens of microseconds)
     t_probe = time.perf_counter()
     while time.perf_counter() - t_probe < 1.5:
-        for _ in range(50):  # this rank's frames only: a time-based loop must not contain collectives (ranks would disagree on the count)
+        for _ in range(50):  # this rank's frames only: a time-based loop must not contain cross-rank waits
             api.render_frame_device(batch, vp, cam.position, cfg_async, VD, ctx)
         ctx.synchronize()
     clocks = sampler.stop()
-    if dist is not None:
-        dist.barrier()
+    barrier()
     torch.cuda.synchronize()
-    total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    if dist is not None:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / K
+    ms_per_step = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(starts, ends))) / K
     fps = 1000.0 / ms_per_step
     api.frame_stats(ctx)  # surfaces an overflow of an async frame, if any
 
-    # ---- chunk-sharded remesh sweep (BASELINE cfg 4): rank r re-meshes the chunks k with k % N == r; the world's voxel
-    #      array is replicated, so halos need no exchange and there is no collective on the path (weak in the sense
-    #      that more GPUs are for more chunks; here the world is fixed, so the line is total chunks / max time)
-    from differential_projection_voxel_renderer_b200 import sharding
-    sub_ids = sharding.chunk_shard(n_chunks, rank, world_size)
-    d_sub = torch.from_numpy(sub_ids).to(dev)
-    sub_batch = api.BinaryGreedyMesher.mesh_batch_subset(d_vox.data_ptr(), d_pos.data_ptr(), d_nb.data_ptr(), 0, n_chunks,
-                                                         d_sub.data_ptr(), int(sub_ids.size), ctx)
+    # ---- N > 1 guards (outside the timed region): the composed frame equals this GPU's own full frame, bit for bit;
+    #      the assembled batch equals a locally meshed one ------------------------------------------------------------
+    if comp is not None:
+        k = frame_no
+        comp.render(batch, vp, cam.position, cfg, VD, k)
+        frame_no += 1
+        if rank == 0:
+            comp.complete(k)
+            ctx.synchronize()
+            comp.check()
+            got_c = comp.frame_tensor(k, dev).cpu().numpy().view(np.uint32)
+            got_d = comp.depth_tensor(k, dev).cpu().numpy().view(np.uint32)
+            comp.release(k)
+            local = mesh_full_locally()
+            api.render_frame_device(local, vp, cam.position, cfg, VD, ctx)
+            dc, dd, rows_, width_ = api.framebuffer_device(ctx)
+            ref_c = multigpu.device_bytes_as_tensor(dc, W * H * 4, dev).cpu().numpy().view(np.uint32).reshape(H, W)
+            ref_d = multigpu.device_bytes_as_tensor(dd, W * H * 4, dev).cpu().numpy().view(np.uint32).reshape(H, W)
+            extra["composite_bit_identical"] = bool(np.array_equal(got_c, ref_c) and np.array_equal(got_d, ref_d))
+            extra["composite_covered_pixels"] = int((ref_c != cfg.clear_color).sum())
+            a_, b_ = batch.download(), local.download()
+            same = all(np.array_equal(a_[kk], b_[kk]) for kk in ("quad_count", "slice_offsets", "face_aabb", "has_mesh"))
+            for i in np.flatnonzero(b_["has_mesh"]):
+                same = same and np.array_equal(a_["quads"][int(a_["quad_base"][i]):int(a_["quad_base"][i]) + int(a_["quad_count"][i])],
+                                               b_["quads"][int(b_["quad_base"][i]):int(b_["quad_base"][i]) + int(b_["quad_count"][i])])
+            extra["sharded_batch_bit_identical"] = bool(same)
+            local.release()
+        ctx.synchronize()
+        barrier()
 
-    def remesh_shard():
-        api.BinaryGreedyMesher.mesh_batch_subset(d_vox.data_ptr(), d_pos.data_ptr(), d_nb.data_ptr(), 0, n_chunks,
-                                                 d_sub.data_ptr(), int(sub_ids.size), ctx, batch=sub_batch)
+    # ---- chunk-sharded remesh sweep (BASELINE cfg 4): rank r re-meshes the lattice chunks k with k % N == r, the packed
+    #      shards are all-gathered (NCCL) and every rank rebuilds the full batch -- the exchange is inside the timed region
+    sharded = None
+    if exchange is not None:
+        for _ in range(2):
+            exchange.sweep(d_voxf.data_ptr(), d_posf.data_ptr(), d_nbf.data_ptr(), d_flf.data_ptr())
+        ctx.synchronize()
+        barrier()
+        sh_ms = []
+        for _ in range(10):
+            flush_l2()
+            a, b2 = event_pair(torch)
+            a.record(stream)
+            exchange.sweep(d_voxf.data_ptr(), d_posf.data_ptr(), d_nbf.data_ptr(), d_flf.data_ptr())
+            b2.record(stream)
+            torch.cuda.synchronize()
+            sh_ms.append(a.elapsed_time(b2))
+        shard_ms = max_over_ranks(float(np.mean(sh_ms)))
+        # the same shard without the exchange (what round 1 reported)
+        ne_ms = []
+        for _ in range(10):
+            flush_l2()
+            a, b2 = event_pair(torch)
+            a.record(stream)
+            api.BinaryGreedyMesher.mesh_batch_subset(d_voxf.data_ptr(), d_posf.data_ptr(), d_nbf.data_ptr(), d_flf.data_ptr(), n_lattice,
+                                                     exchange.d_ids.data_ptr(), int(exchange.ids.size), ctx, batch=exchange.shard)
+            b2.record(stream)
+            torch.cuda.synchronize()
+            ne_ms.append(a.elapsed_time(b2))
+        noex_ms = max_over_ranks(float(np.mean(ne_ms)))
+        sharded = {"lattice_chunks": n_lattice, "varied_chunks": n_varied, "ms_with_exchange_max_over_ranks": shard_ms,
+                   "varied_chunks_meshed_per_sec_with_exchange": n_varied / (shard_ms * 1e-3),
+                   "ms_mesh_only_max_over_ranks": noex_ms, "exchanged_bytes_per_rank": int(exchange.exchanged_bytes),
+                   "how": f"chunk id modulo {world_size}; per sweep: mesh kernel on the shard, totals all-gather (ragged sizes), pack, ONE NCCL "
+                          "all_gather_into_tensor of the shard blocks, vx_mesh_batch_assemble_shards on every rank"}
 
-    for _ in range(3):
-        remesh_shard()
-    ctx.synchronize()
-    if dist is not None:
-        dist.barrier()
-    sh_ms = []
-    for _ in range(20):
-        flush_l2()
-        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        remesh_shard()
-        b2.record(stream)
-        torch.cuda.synchronize()
-        sh_ms.append(a.elapsed_time(b2))
-    shard_ms = float(np.mean(sh_ms))
-    if dist is not None:
-        t = torch.tensor([shard_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        shard_ms = float(t.item())
-    sharded_chunks_per_s = n_chunks / (shard_ms * 1e-3)
-    sub_batch.release()
-
-    # ---- the other way to use N GPUs for this metric: every rank renders whole frames (alternate-frame rendering, no
-    #      collective, weak scaling in frames).  Reported next to the stripe-sharded headline, not instead of it.
+    # ---- alternate-frame rendering (every rank renders whole frames, no exchange): context only, not the headline ---------
     afr_fps = None
     if world_size > 1:
-        cfg_full = api.default_frame_config(W, H)
-        api.render_frame_device(batch, vp, cam.position, cfg_full, VD, ctx)  # sizes the scratch for the full frame
-        cfg_full_async = api.VxFrameConfig.from_buffer_copy(cfg_full)
-        cfg_full_async.async_submit = 1
         for _ in range(3):
-            api.render_frame_device(batch, vp, cam.position, cfg_full_async, VD, ctx)
+            api.render_frame_device(batch, vp, cam.position, cfg_async, VD, ctx)
         ctx.synchronize()
-        dist.barrier()
+        barrier()
         torch.cuda.synchronize()
-        a_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-        a_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-        for i in range(K):
+        tot = 0.0
+        prs = [event_pair(torch) for _ in range(K)]
+        for a, b2 in prs:
             flush_l2()
-            a_s[i].record(stream)
-            api.render_frame_device(batch, vp, cam.position, cfg_full_async, VD, ctx)
-            a_e[i].record(stream)
+            a.record(stream)
+            api.render_frame_device(batch, vp, cam.position, cfg_async, VD, ctx)
+            b2.record(stream)
         torch.cuda.synchronize()
-        t_afr = torch.tensor([sum(x.elapsed_time(y) for x, y in zip(a_s, a_e))], dtype=torch.float64, device=dev)
-        dist.all_reduce(t_afr, op=dist.ReduceOp.MAX)
-        afr_fps = world_size * K / (float(t_afr.item()) * 1e-3)
+        tot = sum(a.elapsed_time(b2) for a, b2 in prs)
+        afr_fps = world_size * K / (max_over_ranks(tot) * 1e-3)
         api.frame_stats(ctx)
-        api.render_frame_device(batch, vp, cam.position, cfg, VD, ctx)  # back to this rank's stripe
 
-    # ---- e2e at N > 1: every rank renders its stripe through the device API (VP + camera + config uploaded per call),
-    #      the stripes are gathered to GPU0 over NVLink and rank 0 reads the composed frame back into page-locked host
-    #      memory, every step; wall clock between barriers, max over ranks
+    # ---- e2e at N > 1: VP + camera + config in on every rank, stripes stored into GPU0's frame, GPU0 copies the composed
+    #      ARGB frame into page-locked host memory -- every step; two frames in flight; wall clock, max over ranks ----------
     e2e_multi = None
-    if world_size > 1:
-        frame_dev = torch.empty((world_size * rows_per, W), dtype=torch.int32, device=dev) if rank == 0 else None
-        host_frame = torch.empty((H, W), dtype=torch.int32).pin_memory() if rank == 0 else None
-        gath = [frame_dev[r * rows_per:(r + 1) * rows_per] for r in range(world_size)] if rank == 0 else None
+    if comp is not None:
+        host = [torch.empty((H, W), dtype=torch.int32).pin_memory() for _ in range(2)] if rank == 0 else None
+        evs = [torch.cuda.Event(), torch.cuda.Event()]
 
-        def step_e2e():
-            api.render_frame_into(batch, vp, cam.position, cfg_async, VD, my_stripe.data_ptr(), 0, ctx)
-            with torch.cuda.stream(stream):
-                dist.gather(my_stripe, gath, dst=0)
-                if rank == 0:
-                    host_frame.copy_(frame_dev[:H], non_blocking=True)
-            ctx.synchronize()
+        def e2e_submit(j):
+            nonlocal frame_no
+            k = frame_no
+            comp.render(batch, vp, cam.position, cfg, VD, k)
+            if rank == 0:
+                comp.complete(k)
+                with torch.cuda.stream(stream):
+                    host[j & 1].copy_(comp.frame_tensor(k, dev), non_blocking=True)
+                comp.release(k)
+            evs[j & 1].record(stream)
+            frame_no += 1
 
-        for _ in range(3):
-            step_e2e()
+        for j in range(4):
+            e2e_submit(j)
+        torch.cuda.synchronize()
         ne2e = max(20, min(K, 200))
-        dist.barrier()
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
-        for _ in range(ne2e):
-            step_e2e()
-        dist.barrier()
-        torch.cuda.synchronize()
-        el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        dist.all_reduce(el, op=dist.ReduceOp.MAX)
-        e2e_multi = ne2e / float(el.item())
+        e2e_submit(0)
+        for j in range(1, ne2e):
+            e2e_submit(j)
+            evs[(j - 1) & 1].synchronize()  # frame j - 1 is complete in host memory (rank 0) / submitted (others)
+        evs[(ne2e - 1) & 1].synchronize()
+        el = time.perf_counter() - t0
+        barrier()
+        e2e_multi = ne2e / max_over_ranks(el)
+        comp.check()
+        if rank == 0:
+            extra["e2e_frames_identical"] = bool(torch.equal(host[0], host[1]))
+
+    # ---- BASELINE cfg 5 (3840x2160, view distance 32): 1 GPU, and at N > 1 the stripe frame with / without the composite ---
+    cfg5 = None
+    try:
+        cfg5 = bench_cfg5(torch, api, multigpu, sharding, ctx, stream, dev, rank, world_size, dist, flush_l2, max_over_ranks, barrier)
+    except Exception as e:  # never let the context line break the headline
+        cfg5 = {"error": repr(e)}
+        log("cfg5 failed:", repr(e))
 
     if rank != 0:
-        return finish_distributed(dist)  # waits for rank 0 (which still has the single-rank sections to run)
+        if comp is not None:
+            comp.close()
+        return teardown(torch, dist, ctx, [batch] if exchange is None else [], exchange)
 
+    # =============================== rank 0 only from here ===============================================================
     # ---- warm-L2 back-to-back throughput (how the path is used in a render loop) --------------------------------
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = event_pair(torch)
     nb2b = 200
     ctx.synchronize()
     e0.record(stream)
     for _ in range(nb2b):
-        api.render_frame_device(batch, vp, cam.position, cfg_async, VD, ctx)  # this rank's rows only (no composite) when N > 1
+        api.render_frame_device(batch, vp, cam.position, cfg_async, VD, ctx)
     e1.record(stream)
     torch.cuda.synchronize()
     b2b_ms = e0.elapsed_time(e1) / nb2b
 
-    # ---- per-kernel split (CUDA events inside the library), L2 flushed, 1 GPU worth of work ---------------------
+    # ---- per-kernel split (CUDA events inside the library), L2 flushed: this rank's share of the frame ---------------
     cfg_prof = api.VxFrameConfig.from_buffer_copy(cfg)
+    cfg_prof.stripe_y0, cfg_prof.stripe_rows = (stripes[rank] if world_size > 1 else (0, 0))
     cfg_prof.profile_kernels = 1
     ksum = np.zeros(4)
     nprof = 20
@@ -437,75 +516,71 @@ def run_cuda(args):
     st = api.frame_stats(ctx)
 
     # algorithmic bytes: framebuffer written once (colour u32 + depth f32, clear fused), visible quad
-    # streams + mesh headers read once, chunk table read once + visibility written
-    vis_ids_quads = st.n_quads
-    rows_mine = cfg.stripe_rows if cfg.stripe_rows > 0 else H
+    # streams + mesh headers read once, chunk table read once (16 B) + visibility (4 B) per loaded chunk
+    rows_mine = stripes[rank][1] if world_size > 1 else H
     b_fb = W * rows_mine * 8
-    b_quads = 3 * vis_ids_quads + 936 * st.n_survivors
-    b_cull = 16 * n_chunks + 4 * n_chunks
-    b_frame = b_fb + b_quads + b_cull
+    b_quads = 3 * st.n_quads + 936 * st.n_survivors
+    b_cull = 20 * n_lattice
+    b_frame_full = W * H * 8 + 3 * st_full.n_quads + 936 * st_full.n_survivors + b_cull
     peak, peak_src = measured_peaks()
     top_bytes = {0: b_cull, 1: b_quads, 2: 0, 3: b_fb + b_quads}[top]
     achieved = top_bytes / (kms[top] * 1e-3) / 1e9 if kms[top] > 0 else 0.0
 
-    # ---- e2e through the host API: VP/camera in, ARGB frame out into pinned host memory, every step -------------
-    # api.FrameLoop binds the framebuffer (device-mapped page-locked host memory the raster kernel writes in place) and the
-    # draw list once; a frame is then one vx_render_frame call
-    e2e_val = None
+    # ---- e2e through the host API at N = 1: api.FrameLoop, pipelined (vx_render_frame_begin / _end): VP + camera + config in,
+    #      the ARGB frame + draw order land in page-locked host memory EVERY step; frame k + 1 is enqueued before the host waits
+    #      for frame k (main.rs:320-336 overlaps present and the next iteration the same way) -----------------------------------
     h2d = 16 * 4 + 3 * 4 + C.sizeof(api.VxFrameConfig)
-    d2h = W * H * 4 + 4 * n_chunks + 64  # frame + draw order + control block
+    d2h = W * H * 4 + 4 * n_lattice + 64  # frame + draw order + control block
+    e2e_val, e2e_sync, e2e_note = None, None, None
     if world_size == 1:
         loop = api.FrameLoop(batch, cfg, view_distance=VD, want_depth=False, ctx=ctx)
         for _ in range(3):
-            loop.render(vp, cam.position)
+            c_sync, _, s_sync = loop.render(vp, cam.position)
+        ref_frame, ref_order = c_sync.copy(), s_sync.copy()
         ne2e = max(20, min(K, 200))
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.synchronize()
         t0 = time.perf_counter()
-        s0.record(stream)
         for _ in range(ne2e):
             loop.render(vp, cam.position)
-        s1.record(stream)
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        e2e_ms = max(s0.elapsed_time(s1), wall * 1000.0) / ne2e
-        e2e_val = 1000.0 / e2e_ms
-        # extra (not the headline): the same frames double-buffered -- frame k is enqueued (vx_render_frame_into, async
-        # submit, into one of two mapped host framebuffers) before the host waits for frame k-1, so launch latency and the
-        # host wake-up hide behind the GPU; every frame still lands in host memory
-        try:
-            bufs = [loop.color, ctx.host_array((H, W), np.uint32)]
-            bufs[1][...] = 0
-            evs = [torch.cuda.Event(), torch.cuda.Event()]
-            ptrs = [int(b.ctypes.data) for b in bufs]
-
-            def submit(k):
-                api.render_frame_into(batch, vp, cam.position, cfg_async, VD, ptrs[k & 1], 0, ctx)
-                evs[k & 1].record(stream)
-
-            for k in range(4):
-                submit(k)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            submit(0)
-            for k in range(1, ne2e):
-                submit(k)
-                evs[(k - 1) & 1].synchronize()
-            evs[(ne2e - 1) & 1].synchronize()
-            e2e_pipelined = ne2e / (time.perf_counter() - t0)
-            if not np.array_equal(bufs[0], bufs[1]):
-                e2e_pipelined = None
-            api.frame_stats(ctx)  # surfaces any deferred scratch overflow of the async frames
-        except Exception as ex:  # noqa: BLE001 -- an extra must never cost the headline line
-            print("pipelined e2e skipped:", ex, file=sys.stderr)
-            e2e_pipelined = None
+        e2e_sync = ne2e / (time.perf_counter() - t0)
+        for _ in range(2):
+            loop.wait(loop.submit(vp, cam.position))
+        ok = True
+        t0 = time.perf_counter()
+        prev = loop.submit(vp, cam.position)
+        for _ in range(1, ne2e):
+            nxt = loop.submit(vp, cam.position)
+            c_, _, s_ = loop.wait(prev)  # frame `prev` is complete in host memory here
+            prev = nxt
+        c_, _, s_ = loop.wait(prev)
+        e2e_val = ne2e / (time.perf_counter() - t0)
+        ok = bool(np.array_equal(c_, ref_frame) and np.array_equal(s_, ref_order))
+        extra["e2e_pipelined_frames_identical_to_synchronous"] = ok
+        extra["e2e_synchronous_frames_per_s"] = e2e_sync
+        if not ok:
+            e2e_val = e2e_sync
+        e2e_note = ("api.FrameLoop.submit / wait -> vx_render_frame_begin / _end: VP + camera + config in; the ARGB frame (written over PCIe by the "
+                    "raster kernel itself into device-mapped page-locked memory, no staging copy) and the draw order land in host memory every "
+                    "step; two frames in flight (frame k+1 is enqueued before the host waits for frame k); colour only -- the depth plane is "
+                    "frame-internal (the reference presents color_buffer only, main.rs:320-322); extra.e2e_synchronous_frames_per_s = one "
+                    "blocking vx_render_frame per step")
     else:
         e2e_val = e2e_multi
-        e2e_pipelined = None
+        e2e_note = ("per step every rank gets VP + camera + config and renders its stripe (vx_render_frame_into) straight into GPU0's frame over "
+                    "NVLink; GPU0 waits for the arrival flags, copies the composed ARGB frame to page-locked host memory, acknowledges; two frames "
+                    "in flight; wall clock between barriers, max over ranks")
 
-    # ---- second BASELINE metric: chunks meshed / s (whole-world remesh sweep, inputs resident) -------------------
+    # ---- second BASELINE metric: chunks meshed / s (whole-world remesh sweep of the Varied chunks, inputs resident) ----
+    d_vox = torch.from_numpy(v).to(dev)
+    d_nb = torch.from_numpy(nb).to(dev)
+    d_pos = torch.from_numpy(p).to(dev)
+    hv = C.c_void_p()
+    ctx.check(ctx.lib.vx_mesh_chunks_device(ctx.handle, C.c_void_p(d_vox.data_ptr()), C.c_void_p(d_pos.data_ptr()), C.c_void_p(d_nb.data_ptr()),
+                                            None, n_varied, C.byref(hv)))
+    vbatch = api.MeshBatch(ctx, hv)
+
     def remesh():
-        ctx.check(ctx.lib.vx_remesh_chunks_device(ctx.handle, C.c_void_p(d_vox.data_ptr()), C.c_void_p(d_nb.data_ptr()), None, batch.handle))
+        ctx.check(ctx.lib.vx_remesh_chunks_device(ctx.handle, C.c_void_p(d_vox.data_ptr()), C.c_void_p(d_nb.data_ptr()), None, vbatch.handle))
 
     for _ in range(3):
         remesh()
@@ -513,22 +588,22 @@ def run_cuda(args):
     m_ms = []
     for _ in range(20):
         flush_l2()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a, b = event_pair(torch)
         a.record(stream)
         remesh()
         b.record(stream)
         torch.cuda.synchronize()
         m_ms.append(a.elapsed_time(b))
     mesh_ms = float(np.mean(m_ms))
-    chunks_per_s = n_chunks / (mesh_ms * 1e-3)
+    chunks_per_s = n_varied / (mesh_ms * 1e-3)
     n_nbr = int((nb >= 0).sum())
-    b_mesh = n_chunks * (32768 + 792 + 144) + 1024 * n_nbr + 3 * total_quads
+    b_mesh = n_varied * (32768 + 792 + 144) + 1024 * n_nbr + 3 * total_quads
     mesh_gbs = b_mesh / (mesh_ms * 1e-3) / 1e9
 
     # large-batch meshing (BASELINE cfg 1 replicated: one terrain chunk, no neighbours, 16,384 copies = 512 MiB > L2), for the
     # chunk with the most quads of the world (worst case of the sweep) and for the median one
     rep = 16384
-    qc_all = batch.download()["quad_count"]
+    qc_all = vbatch.download()["quad_count"]
 
     def big_batch(idx):
         d_big = d_vox[idx].repeat(rep, 1).contiguous()
@@ -538,7 +613,7 @@ def run_cuda(args):
         quads = int(big.info().total_quads)
         bm = []
         for _ in range(5):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a, b = event_pair(torch)
             a.record(stream)
             ctx.check(ctx.lib.vx_remesh_chunks_device(ctx.handle, C.c_void_p(d_big.data_ptr()), None, None, big.handle))
             b.record(stream)
@@ -552,8 +627,7 @@ def run_cuda(args):
     big_cps, big_gbs, big_q = big_batch(int(np.argmax(qc_all)))
     med_cps, med_gbs, med_q = big_batch(int(np.argsort(qc_all)[len(qc_all) // 2]))
 
-    # ---- meshing end to end in the steady state: the world's voxels come from page-locked host memory every sweep
-    #      (one H2D copy into the resident device array), re-mesh into the existing batch, read the totals back
+    # ---- meshing end to end in the steady state: the world's voxels come from page-locked host memory every sweep ----------
     mesh_e2e = None
     if world_size == 1:
         try:
@@ -563,7 +637,7 @@ def run_cuda(args):
                 with torch.cuda.stream(stream):
                     d_vox.copy_(hv_t, non_blocking=True)
                 remesh()
-                return batch.info().total_quads  # synchronises and reads the totals back
+                return vbatch.info().total_quads  # synchronises and reads the totals back
 
             for _ in range(3):
                 sweep()
@@ -572,214 +646,291 @@ def run_cuda(args):
             for _ in range(reps):
                 tq_e2e = sweep()
             el = (time.perf_counter() - t0) / reps
-            assert int(tq_e2e) == total_quads
-            mesh_e2e = {"chunks_per_sec": n_chunks / el, "ms_per_world": el * 1e3, "h2d_bytes_per_sweep": int(v.nbytes), "d2h_bytes_per_sweep": 32,
-                        "note": "818 x 32 KiB voxels H2D from page-locked memory + vx_remesh_chunks_device + totals read back, wall clock; PCIe-bound"}
+            mesh_e2e = {"chunks_per_sec": n_varied / el, "ms_per_world": el * 1e3, "h2d_bytes_per_sweep": int(v.nbytes), "d2h_bytes_per_sweep": 32,
+                        "quads": int(tq_e2e),
+                        "note": f"{n_varied} x 32 KiB voxels H2D from page-locked memory + vx_remesh_chunks_device + totals read back, wall clock; PCIe-bound"}
+            del hv_t
         except Exception as e:
             mesh_e2e = {"error": repr(e)}
 
-    # ---- terrain generated on the device and meshed without ever crossing PCIe: all 7,153 lattice chunks
+    # ---- terrain generated on the device and meshed without ever crossing PCIe: all lattice chunks --------
     gen_mesh = None
     if world_size == 1:
         try:
-            nb_full = world.neighbor_table()
-            d_posf = torch.from_numpy(pos).to(dev)
-            d_nbf = torch.from_numpy(nb_full).to(dev)
-            d_voxf = torch.empty((pos.shape[0], 32768), dtype=torch.uint8, device=dev)
+            d_voxg = torch.empty((n_lattice, 32768), dtype=torch.uint8, device=dev)
             tp = api.terrain_params()
-            fl = api.generate_terrain(pos, d_voxf.data_ptr(), ctx, tp)
-            d_flf = torch.from_numpy(fl).to(dev)
+            fl = api.generate_terrain(pos, d_voxg.data_ptr(), ctx, tp)
+            d_flg = torch.from_numpy(fl).to(dev)
             hh = C.c_void_p()
-            ctx.check(ctx.lib.vx_mesh_chunks_device(ctx.handle, C.c_void_p(d_voxf.data_ptr()), C.c_void_p(d_posf.data_ptr()),
-                                                    C.c_void_p(d_nbf.data_ptr()), C.c_void_p(d_flf.data_ptr()), int(pos.shape[0]), C.byref(hh)))
+            ctx.check(ctx.lib.vx_mesh_chunks_device(ctx.handle, C.c_void_p(d_voxg.data_ptr()), C.c_void_p(d_posf.data_ptr()),
+                                                    C.c_void_p(d_nbf.data_ptr()), C.c_void_p(d_flg.data_ptr()), n_lattice, C.byref(hh)))
             bfull = api.MeshBatch(ctx, hh)
-            assert int(bfull.info().total_quads) == total_quads, "device-generated world meshes differently"
+            same_world = int(bfull.info().total_quads) == total_quads
             ctx.synchronize()
             t0 = time.perf_counter()
             reps = 10
             for _ in range(reps):
-                api.generate_terrain(pos, d_voxf.data_ptr(), ctx, tp)
-                ctx.check(ctx.lib.vx_remesh_chunks_device(ctx.handle, C.c_void_p(d_voxf.data_ptr()), C.c_void_p(d_nbf.data_ptr()),
-                                                          C.c_void_p(d_flf.data_ptr()), bfull.handle))
+                api.generate_terrain(pos, d_voxg.data_ptr(), ctx, tp)
+                ctx.check(ctx.lib.vx_remesh_chunks_device(ctx.handle, C.c_void_p(d_voxg.data_ptr()), C.c_void_p(d_nbf.data_ptr()),
+                                                          C.c_void_p(d_flg.data_ptr()), bfull.handle))
             ctx.synchronize()
             el = (time.perf_counter() - t0) / reps
-            gen_mesh = {"chunks": int(pos.shape[0]), "varied_chunks": n_chunks, "ms_per_world": el * 1e3, "lattice_chunks_per_sec": pos.shape[0] / el,
-                        "note": "vx_generate_terrain (7,153 positions -> voxels + Uniform flags on the device) + vx_remesh_chunks_device, wall clock"}
+            gen_mesh = {"chunks": n_lattice, "varied_chunks": n_varied, "ms_per_world": el * 1e3, "lattice_chunks_per_sec": n_lattice / el,
+                        "same_quads_as_host_generated_world": bool(same_world),
+                        "note": "vx_generate_terrain (all lattice positions -> voxels + Uniform flags on the device) + vx_remesh_chunks_device, wall clock"}
             bfull.release()
-            del d_voxf
+            del d_voxg
         except Exception as e:
             gen_mesh = {"error": repr(e)}
 
-    # ---- adjacent rasterizers: the reference's own span-walker bench case and the macrotile frame ---
     a18 = None
     if world_size == 1:
         try:
-            from oracle import binding as ob18
-            sw_w, sw_h = 1920, 1080  # benches/span_walker.rs:36-77 "span_walker_full_packet_32_quads": a 4 x 8 grid of quads
-            ii = np.arange(32)
-            bx0 = (np.float32(-0.9) + (ii % 8).astype(np.float32) * np.float32(0.225)).astype(np.float32)
-            by0 = (np.float32(-0.9) + (ii // 8).astype(np.float32) * np.float32(0.45)).astype(np.float32)
-            bx1 = (bx0 + np.float32(0.2)).astype(np.float32)
-            by1 = (by0 + np.float32(0.4)).astype(np.float32)
-            bz = np.full(32, 0.5, dtype=np.float32)
-            bt = ((ii % 4) + 1).astype(np.uint8)
-            d_boxes = torch.from_numpy(np.concatenate([bx0, by0, bx1, by1, bz])).to(dev)
-            d_types = torch.from_numpy(np.concatenate([bt, np.ones(32, dtype=np.uint8)])).to(dev)
-            d_col = torch.zeros((sw_h, sw_w), dtype=torch.int32, device=dev)
-            d_dep = torch.full((sw_h, sw_w), float("inf"), dtype=torch.float32, device=dev)
-
-            def walk():
-                ctx.check(ctx.lib.vx_span_walk_quads_device(ctx.handle, C.c_void_p(d_boxes.data_ptr()), C.c_void_p(d_types.data_ptr()), 32, sw_w, sw_h,
-                                                            C.c_void_p(d_col.data_ptr()), C.c_void_p(d_dep.data_ptr())))
-
-            walk()  # first call draws; the repeats below re-test equal depths like the reference's bench loop does
-            ctx.synchronize()
-            oc18 = np.zeros((sw_h, sw_w), dtype=np.uint32)
-            od18 = np.full((sw_h, sw_w), np.inf, dtype=np.float32)
-            ob18.span_walk_quads(oc18, od18, bx0, by0, bx1, by1, bz, bt)
-            same18 = bool(np.array_equal(d_col.cpu().numpy().view(np.uint32), oc18))
-            sw_ms = []
-            for _ in range(10):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(stream)
-                walk()
-                b.record(stream)
-                torch.cuda.synchronize()
-                sw_ms.append(a.elapsed_time(b))
-            t0 = time.perf_counter()
-            for _ in range(5):
-                ob18.span_walk_quads(oc18, od18, bx0, by0, bx1, by1, bz, bt)
-            sw_cpu_ms = (time.perf_counter() - t0) / 5 * 1e3
-            # macrotile frame of the headline scene: caller's list = every meshed chunk that passes filter A
-            vis18 = api.get_visible_chunks_frustum(p, cam.position, vp, VD, True, ctx)
-            ids18 = np.flatnonzero((vis18 != 0) & (qc_all > 0)).astype(np.int32)
-            cfg_m = api.VxFrameConfig.from_buffer_copy(cfg)
-            cfg_m.macrotile = 1
-            cfg_m.async_submit = 0
-            mt_ms = []
-            api.render_frame(batch, vp, cam.position, cfg_m, mesh_ids=ids18, ctx=ctx)
-            for _ in range(10):
-                t0 = time.perf_counter()
-                api.render_frame(batch, vp, cam.position, cfg_m, mesh_ids=ids18, want_depth=False, color_out=loop.color, ctx=ctx)
-                mt_ms.append((time.perf_counter() - t0) * 1e3)
-            # Hyper-Pipeline (benches/differential_projection.rs:8-36 scene; host framebuffers in and out, wall clock)
-            import vx_kat
-            hb = api.BinaryGreedyMesher.mesh_batch(vx_kat.chunk_slab().reshape(1, -1), [(0, 0, 0)], None, None, ctx)
-            from differential_projection_voxel_renderer_b200 import camera as _cam
-            hvp = _cam.mat4_mul(_cam.perspective_rh(np.radians(np.float32(70.0)), 16 / 9, 0.1, 1000.0),
-                                _cam.look_at_rh((64.0, 50.0, 100.0), (64.0, 32.0, 64.0), (0.0, 1.0, 0.0))).reshape(16)
-            hfb = api.Framebuffer(1280, 720)
-            hyper_quads = api.hyper_pipeline_render(hb, [0], hvp, hfb, ctx)
-            hp_ms = []
-            for _ in range(5):
-                hfb = api.Framebuffer(1280, 720)
-                t0 = time.perf_counter()
-                api.hyper_pipeline_render(hb, [0], hvp, hfb, ctx)
-                hp_ms.append((time.perf_counter() - t0) * 1e3)
-            hb.release()
-            a18 = {"hyper_pipeline_1280x720_one_chunk_ms": float(np.median(hp_ms)), "hyper_pipeline_visible_quads": hyper_quads,
-                   "span_walker_full_packet_32_quads_1920x1080_ms": float(np.median(sw_ms)), "span_walker_cpu_port_ms": sw_cpu_ms,
-                   "span_walker_matches_oracle": same18, "span_walker_launches": 5,
-                   "macrotile_frame_1280x720_vd12_e2e_ms": float(np.median(mt_ms)), "macrotile_meshes": int(ids18.size),
-                   "note": "vx_span_walk_quads_device (benches/span_walker.rs:36-77 workload, framebuffer resident) and vx_render_frame with cfg.macrotile = 1 (render_frame_macrotile) through the host API into mapped host memory, wall clock"}
+            a18 = bench_adjacent(torch, api, ctx, stream, dev, vbatch, p, qc_all, vp, cam, cfg, loop)
         except Exception as e:  # noqa: BLE001
             a18 = {"error": repr(e)}
 
-    # ---- BASELINE cfg 5 on this one GPU (context for the multi-GPU design point): 3840x2160, view distance 32 ------------
-    cfg5 = None
-    if world_size == 1:
-        try:
-            import vx_scenes
-            pos5, world5, p5, v5, nb5 = vx_scenes.terrain_scene(32)
-            batch5 = api.BinaryGreedyMesher.mesh_batch(v5, p5, nb5, None, ctx)
-            cam5 = vx_scenes.main_camera(3840, 2160)
-            vp5 = cam5.view_projection()
-            c5 = api.default_frame_config(3840, 2160)
-            api.render_frame_device(batch5, vp5, cam5.position, c5, 32, ctx)
-            c5a = api.VxFrameConfig.from_buffer_copy(c5)
-            c5a.async_submit = 1
-            for _ in range(3):
-                api.render_frame_device(batch5, vp5, cam5.position, c5a, 32, ctx)
-            t5 = []
-            for _ in range(20):
-                flush_l2()
-                a5, b5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a5.record(stream)
-                api.render_frame_device(batch5, vp5, cam5.position, c5a, 32, ctx)
-                b5.record(stream)
-                torch.cuda.synchronize()
-                t5.append(a5.elapsed_time(b5))
-            st5 = api.frame_stats(ctx)
-            ms5 = float(np.mean(t5))
-            bytes5 = 3840 * 2160 * 8 + 3 * st5.n_quads + 936 * st5.n_survivors + 20 * int(p5.shape[0])
-            cfg5 = {"workload": "3840x2160 view distance 32 (137,065 lattice chunks), 1 GPU, L2 flushed", "frame_ms": ms5, "frames_per_sec": 1000.0 / ms5,
-                    "varied_chunks": int(p5.shape[0]), "visible_meshes": int(st5.n_survivors), "visible_quads": int(st5.n_quads),
-                    "triangles": int(st5.n_triangles), "algorithmic_bytes": int(bytes5), "hbm_frac": bytes5 / (ms5 * 1e-3) / 1e9 / peak}
-            batch5.release()
-            del v5
-        except Exception as e:  # never let the context line break the headline
-            cfg5 = {"error": repr(e)}
-
     # ---- CPU baseline beside it (bounded sample) -------------------------------------------------------------------
     threads = os.cpu_count() or 1
-    cpu_fps, cpu_n, cpu_el = cpu_frame_baseline(p, v, nb, cam, 10.0, threads)
+    cpu_fps, cpu_n, cpu_el, _ = cpu_frame_baseline(sc, 10.0, threads)
     cpu_cps, cpu_mn, cpu_mel = cpu_mesh_baseline(v, nb, 3.0)
 
+    traffic = ncu_traffic(knames[top]) if world_size == 1 else None  # the committed capture is the 1-GPU full frame
+    extra.update({
+        "frame_ms_warm_l2_back_to_back": b2b_ms, "frames_per_sec_warm_l2": 1000.0 / b2b_ms,
+        "kernel_ms": {k: float(x) for k, x in zip(knames, kms)},
+        "kernel_ms_note": "CUDA events around each kernel (profile mode serialises them; the async path overlaps them by programmatic dependent launch)"
+                          + ("" if world_size == 1 else "; rank 0's stripe"),
+        "launches_per_step": launches_per_frame,
+        "frame_stats": {"visible_meshes": int(st_full.n_survivors), "visible_quads": int(st_full.n_quads), "triangles": int(st_full.n_triangles),
+                        "bin_entries": int(st_full.n_bin_entries)},
+        "stripes": [list(s) for s in stripes],
+        "frame_algorithmic_bytes": int(b_frame_full), "frame_hbm_frac": (b_frame_full / (ms_per_step * 1e-3) / 1e9) / peak,
+        "chunks_meshed_per_sec": chunks_per_s, "remesh_world_ms": mesh_ms, "remesh_world_chunks": n_varied,
+        "remesh_algorithmic_GBps": mesh_gbs, "remesh_hbm_frac": mesh_gbs / peak,
+        "remesh_sharded": sharded,
+        "chunks_meshed_per_sec_large_batch": big_cps, "large_batch": f"{rep} copies of the world's busiest terrain chunk ({big_q} quads), no neighbours (BASELINE configs[0] replicated, 512 MiB of voxels)",
+        "chunks_meshed_per_sec_large_batch_median_chunk": med_cps, "median_chunk_quads": med_q,
+        "large_batch_median_algorithmic_GBps": med_gbs, "large_batch_median_hbm_frac": med_gbs / peak,
+        "large_batch_algorithmic_GBps": big_gbs, "large_batch_hbm_frac": big_gbs / peak,
+        "cpu_chunks_meshed_per_sec_1_thread": cpu_cps,
+        "cfg5_3840x2160_vd32": cfg5,
+        "mesh_e2e_steady_state": mesh_e2e,
+        "generate_and_mesh_on_device": gen_mesh,
+        "adjacent_rasterizers_a18": a18,
+        "frames_per_sec_alternate_frame_rendering": afr_fps,
+        "alternate_frame_rendering": "N > 1 only: every GPU renders whole 1280x720 frames independently (no exchange), total frames / max time over ranks; context, not the headline",
+        "reference_published": "162-168 fps on a 6-core i5-12400 (README.md:29-32)",
+    })
     out = {
-        "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world_size, "steps": K, "warmup": max(3, args.warmup),
+        "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world_size, "steps": K, "warmup": Wm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "full frame 1280x720 view distance 12 (filter A + filter B/sort + project/clip/cull + span raster), "
-                               "meshes cached on device; BASELINE.json configs[2]",
-                   "chunks": int(pos.shape[0]), "varied_chunks": n_chunks, "total_quads": total_quads,
-                   "visible_meshes": int(st.n_survivors), "visible_quads": int(st.n_quads), "triangles": int(st.n_triangles),
-                   "camera": "(0,10,20) yaw 0 pitch 0 fov 70", "projection": "exact (bit-identical to the CPU path)",
-                   "l2": "flushed between timed frames (256 MiB device write, outside the timed events)",
-                   "parallelism": "1 GPU" if world_size == 1 else f"{world_size} screen stripes of {rows_per} rows, NCCL gather to GPU0"},
+        "config": workload_config(world_size, sc, total_quads),
         "clocks": clocks,
         "gpu_launches": int(l1 - l0),
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "note": ("per step every rank renders its stripe (vx_render_frame_device), NCCL gather to GPU0, rank 0 copies the composed ARGB frame to page-locked host memory; wall clock between barriers, max over ranks" if world_size > 1 else "api.FrameLoop.render -> vx_render_frame, one synchronous call per frame: VP + camera + config in; the ARGB frame lands in page-locked host memory (written over PCIe by the raster kernel itself, no staging copy) together with the draw order; the call returns after the stream has drained")},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "note": e2e_note},
         "roofline": {"bound": "hbm", "kernel": knames[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic(knames[top]), "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(top_bytes), "kernel_ms": float(kms[top]),
                      "kernel_share_of_step": float(kms[top] / kms.sum()) if kms.sum() > 0 else None},
         "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{cpu_n} full 1280x720 vd12 frames in {cpu_el:.1f} s; C restatement of the reference CPU path "
-                                   "(oracle/), stripe-parallel over all host threads (the Rust crate cannot be built here: no cargo)"},
-        "extra": {
-            "frame_ms_warm_l2_back_to_back": b2b_ms, "frames_per_sec_warm_l2": 1000.0 / b2b_ms,
-            "kernel_ms": {k: float(x) for k, x in zip(knames, kms)},
-            "launches_per_frame": int(launches_per_frame),
-            "frame_algorithmic_bytes": int(b_frame), "frame_hbm_frac": (b_frame / (ms_per_step * 1e-3) / 1e9) / peak,
-            "chunks_meshed_per_sec": chunks_per_s, "remesh_world_ms": mesh_ms, "remesh_world_chunks": n_chunks,
-            "chunks_meshed_per_sec_sharded": sharded_chunks_per_s, "remesh_sharded_ms_max_over_ranks": shard_ms,
-            "remesh_sharding": f"chunk id modulo {world_size} GPUs, voxels replicated, no collective",
-            "remesh_algorithmic_GBps": mesh_gbs, "remesh_hbm_frac": mesh_gbs / peak,
-            "chunks_meshed_per_sec_large_batch": big_cps, "large_batch": f"{rep} copies of the world's busiest terrain chunk ({big_q} quads), no neighbours (BASELINE configs[0] replicated, 512 MiB of voxels)",
-            "chunks_meshed_per_sec_large_batch_median_chunk": med_cps, "median_chunk_quads": med_q,
-            "large_batch_median_algorithmic_GBps": med_gbs, "large_batch_median_hbm_frac": med_gbs / peak,
-            "large_batch_algorithmic_GBps": big_gbs, "large_batch_hbm_frac": big_gbs / peak,
-            "cpu_chunks_meshed_per_sec_1_thread": cpu_cps,
-            "cfg5_3840x2160_vd32": cfg5,
-            "mesh_e2e_steady_state": mesh_e2e,
-            "e2e_double_buffered_frames_per_s": round(e2e_pipelined, 1) if e2e_pipelined else None,
-            "generate_and_mesh_on_device": gen_mesh,
-            "adjacent_rasterizers_a18": a18,
-            "frames_per_sec_alternate_frame_rendering": afr_fps,
-            "alternate_frame_rendering": "N > 1 only: every GPU renders whole 1280x720 frames independently (no collective), total frames / max time over ranks; the headline value is the stripe-sharded single frame (strong scaling)",
-            "reference_published": "162-168 fps on a 6-core i5-12400 (README.md:29-32)",
-        },
+                                   f"(oracle/), stripe-parallel over all {threads} host threads; " + cargo_note()},
+        "extra": extra,
     }
     emit_json_line(out)
-    if dist is not None:
-        return finish_distributed(dist)
-    # The context (and with it the stream torch's allocators have recorded events on) is deliberately NOT torn down
-    # here: freeing the torch tensors after the stream is gone aborts the process.  Leave at once; the driver owns
-    # the process lifetime.
-    sys.stdout.flush()
-    sys.stderr.flush()
-    os._exit(0)
+    if world_size == 1:
+        del loop
+    vbatch.release()
+    if comp is not None:
+        comp.close()
+    return teardown(torch, dist, ctx, [batch] if exchange is None else [], exchange)
+
+
+def teardown(torch, dist, ctx, batches, exchange):
+    """Orderly exit: device work drained, library objects released while the context is alive, torch's cached blocks freed
+    before the context's stream goes away, process group destroyed -- then main() leaves through the normal exit path."""
+    rc = 0
+    try:
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        for b in batches:
+            b.release()
+        if exchange is not None:
+            exchange.close()
+        if dist is not None:
+            dist.barrier()
+    except Exception as e:  # noqa: BLE001
+        log("teardown:", repr(e))
+        rc = 1
+    return rc
+
+
+def bench_cfg5(torch, api, multigpu, sharding, ctx, stream, dev, rank, world_size, dist, flush_l2, max_over_ranks, barrier):
+    """3840x2160 view distance 32 (137,065 lattice chunks; the Varied ones are meshed on every rank): one GPU renders the whole
+    frame; N GPUs render work-balanced stripes, timed with and without the peer-store composite."""
+    import vx_scenes
+    W5, H5, VD5 = 3840, 2160, 32
+    pos5, world5, p5, v5, nb5 = vx_scenes.terrain_scene(VD5)
+    batch5 = api.BinaryGreedyMesher.mesh_batch(v5, p5, nb5, None, ctx, validate=False)
+    cam5 = vx_scenes.main_camera(W5, H5)
+    vp5 = cam5.view_projection()
+    c5 = api.default_frame_config(W5, H5)
+    api.render_frame_device(batch5, vp5, cam5.position, c5, VD5, ctx)
+    st5 = api.frame_stats(ctx)
+    c5a = api.VxFrameConfig.from_buffer_copy(c5)
+    c5a.async_submit = 1
+    peak, _ = measured_peaks()
+    bytes5 = W5 * H5 * 8 + 3 * st5.n_quads + 936 * st5.n_survivors + 20 * int(p5.shape[0])
+    out = {"workload": "3840x2160 view distance 32 (137,065 lattice chunks, Varied ones meshed with neighbours), L2 flushed",
+           "varied_chunks": int(p5.shape[0]), "visible_meshes": int(st5.n_survivors), "visible_quads": int(st5.n_quads),
+           "triangles": int(st5.n_triangles), "algorithmic_bytes": int(bytes5)}
+
+    def timed(fn, n=20):
+        for _ in range(3):
+            fn()
+        ctx.synchronize()
+        barrier()
+        prs = []
+        for _ in range(n):
+            flush_l2()
+            a, b = event_pair(torch)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            prs.append((a, b))
+        torch.cuda.synchronize()
+        return max_over_ranks(sum(a.elapsed_time(b) for a, b in prs)) / n
+
+    if world_size == 1:
+        ms5 = timed(lambda: api.render_frame_device(batch5, vp5, cam5.position, c5a, VD5, ctx))
+        out.update({"frame_ms": ms5, "frames_per_sec": 1000.0 / ms5, "hbm_frac": bytes5 / (ms5 * 1e-3) / 1e9 / peak})
+    else:
+        band = api.frame_bin_counts(ctx).sum(axis=1).astype(np.float64)
+        holder = [sharding.balanced_stripes(band, H5, world_size, band=8, row_cost=float(band.sum()) / (4.0 * H5))] if rank == 0 else [None]
+        dist.broadcast_object_list(holder, src=0)
+        stripes5 = [tuple(x) for x in holder[0]]
+        # (a) every rank renders the whole frame (= the 1-GPU time on this box)
+        ms_one = timed(lambda: api.render_frame_device(batch5, vp5, cam5.position, c5a, VD5, ctx))
+        # (b) stripes into local memory, no composite
+        cs = api.VxFrameConfig.from_buffer_copy(c5a)
+        cs.stripe_y0, cs.stripe_rows = stripes5[rank]
+        ms_stripe = timed(lambda: api.render_frame_device(batch5, vp5, cam5.position, cs, VD5, ctx)) if stripes5[rank][1] > 0 else timed(lambda: None)
+        # (c) stripes stored into GPU0's frame over NVLink + arrival flags
+        comp5 = multigpu.StripeCompositor(ctx, W5, H5, rank, world_size, want_depth=True)
+        comp5.set_stripes(stripes5)
+        kk = [0]
+
+        def step():
+            comp5.render(batch5, vp5, cam5.position, c5, VD5, kk[0])
+            if rank == 0:
+                comp5.complete(kk[0])
+                comp5.release(kk[0])
+            kk[0] += 1
+
+        ms_comp = timed(step)
+        comp5.check()
+        # guard: composed frame == this GPU's own whole frame
+        k = kk[0]
+        comp5.render(batch5, vp5, cam5.position, c5, VD5, k)
+        same = None
+        if rank == 0:
+            comp5.complete(k)
+            ctx.synchronize()
+            got_c = comp5.frame_tensor(k, dev).cpu().numpy().view(np.uint32)
+            got_d = comp5.depth_tensor(k, dev).cpu().numpy().view(np.uint32)
+            comp5.release(k)
+            api.render_frame_device(batch5, vp5, cam5.position, c5, VD5, ctx)
+            dc, dd, _, _ = api.framebuffer_device(ctx)
+            ref_c = multigpu.device_bytes_as_tensor(dc, W5 * H5 * 4, dev).cpu().numpy().view(np.uint32).reshape(H5, W5)
+            ref_d = multigpu.device_bytes_as_tensor(dd, W5 * H5 * 4, dev).cpu().numpy().view(np.uint32).reshape(H5, W5)
+            same = bool(np.array_equal(got_c, ref_c) and np.array_equal(got_d, ref_d))
+        ctx.synchronize()
+        barrier()
+        comp5.close()
+        out.update({"n_gpus": world_size, "stripes": [list(s) for s in stripes5],
+                    "frame_ms_one_gpu_whole_frame": ms_one, "frame_ms_stripes_no_composite": ms_stripe,
+                    "frame_ms": ms_comp, "frames_per_sec": 1000.0 / ms_comp, "composite_bit_identical": same,
+                    "hbm_frac_per_gpu": bytes5 / world_size / (ms_comp * 1e-3) / 1e9 / peak,
+                    "note": "frame_ms = work-balanced stripes, every raster kernel stores its rows (colour + depth) into GPU0's frame over NVLink, "
+                            "GPU0 waits for the arrival flags; max over ranks"})
+    api.frame_stats(ctx)
+    batch5.release()
+    del v5, world5
+    return out
+
+
+def bench_adjacent(torch, api, ctx, stream, dev, batch, p, qc_all, vp, cam, cfg, loop):
+    """Adjacent rasterizers: the reference's own span-walker bench case, the macrotile frame, the Hyper-Pipeline."""
+    from oracle import binding as ob18
+    sw_w, sw_h = 1920, 1080  # benches/span_walker.rs:36-77 "span_walker_full_packet_32_quads": a 4 x 8 grid of quads
+    ii = np.arange(32)
+    bx0 = (np.float32(-0.9) + (ii % 8).astype(np.float32) * np.float32(0.225)).astype(np.float32)
+    by0 = (np.float32(-0.9) + (ii // 8).astype(np.float32) * np.float32(0.45)).astype(np.float32)
+    bx1 = (bx0 + np.float32(0.2)).astype(np.float32)
+    by1 = (by0 + np.float32(0.4)).astype(np.float32)
+    bz = np.full(32, 0.5, dtype=np.float32)
+    bt = ((ii % 4) + 1).astype(np.uint8)
+    d_boxes = torch.from_numpy(np.concatenate([bx0, by0, bx1, by1, bz])).to(dev)
+    d_types = torch.from_numpy(np.concatenate([bt, np.ones(32, dtype=np.uint8)])).to(dev)
+    d_col = torch.zeros((sw_h, sw_w), dtype=torch.int32, device=dev)
+    d_dep = torch.full((sw_h, sw_w), float("inf"), dtype=torch.float32, device=dev)
+
+    def walk():
+        ctx.check(ctx.lib.vx_span_walk_quads_device(ctx.handle, C.c_void_p(d_boxes.data_ptr()), C.c_void_p(d_types.data_ptr()), 32, sw_w, sw_h,
+                                                    C.c_void_p(d_col.data_ptr()), C.c_void_p(d_dep.data_ptr())))
+
+    walk()  # first call draws; the repeats below re-test equal depths like the reference's bench loop does
+    ctx.synchronize()
+    oc18 = np.zeros((sw_h, sw_w), dtype=np.uint32)
+    od18 = np.full((sw_h, sw_w), np.inf, dtype=np.float32)
+    ob18.span_walk_quads(oc18, od18, bx0, by0, bx1, by1, bz, bt)
+    same18 = bool(np.array_equal(d_col.cpu().numpy().view(np.uint32), oc18))
+    sw_ms = []
+    for _ in range(10):
+        a, b = event_pair(torch)
+        a.record(stream)
+        walk()
+        b.record(stream)
+        torch.cuda.synchronize()
+        sw_ms.append(a.elapsed_time(b))
+    t0 = time.perf_counter()
+    for _ in range(5):
+        ob18.span_walk_quads(oc18, od18, bx0, by0, bx1, by1, bz, bt)
+    sw_cpu_ms = (time.perf_counter() - t0) / 5 * 1e3
+    # macrotile frame of the headline scene: caller's list = every meshed chunk that passes filter A
+    vis18 = api.get_visible_chunks_frustum(p, cam.position, vp, VD, True, ctx)
+    ids18 = np.flatnonzero((vis18 != 0) & (qc_all > 0)).astype(np.int32)
+    cfg_m = api.VxFrameConfig.from_buffer_copy(cfg)
+    cfg_m.macrotile = 1
+    cfg_m.async_submit = 0
+    mt_ms = []
+    api.render_frame(batch, vp, cam.position, cfg_m, mesh_ids=ids18, ctx=ctx)
+    for _ in range(10):
+        t0 = time.perf_counter()
+        api.render_frame(batch, vp, cam.position, cfg_m, mesh_ids=ids18, want_depth=False, color_out=loop.color, ctx=ctx)
+        mt_ms.append((time.perf_counter() - t0) * 1e3)
+    # Hyper-Pipeline (benches/differential_projection.rs:8-36 scene; host framebuffers in and out, wall clock)
+    import vx_kat
+    hb = api.BinaryGreedyMesher.mesh_batch(vx_kat.chunk_slab().reshape(1, -1), [(0, 0, 0)], None, None, ctx)
+    from differential_projection_voxel_renderer_b200 import camera as _cam
+    hvp = _cam.mat4_mul(_cam.perspective_rh(np.radians(np.float32(70.0)), 16 / 9, 0.1, 1000.0),
+                        _cam.look_at_rh((64.0, 50.0, 100.0), (64.0, 32.0, 64.0), (0.0, 1.0, 0.0))).reshape(16)
+    hfb = api.Framebuffer(1280, 720)
+    hyper_quads = api.hyper_pipeline_render(hb, [0], hvp, hfb, ctx)
+    hp_ms = []
+    for _ in range(5):
+        hfb = api.Framebuffer(1280, 720)
+        t0 = time.perf_counter()
+        api.hyper_pipeline_render(hb, [0], hvp, hfb, ctx)
+        hp_ms.append((time.perf_counter() - t0) * 1e3)
+    hb.release()
+    return {"hyper_pipeline_1280x720_one_chunk_ms": float(np.median(hp_ms)), "hyper_pipeline_visible_quads": hyper_quads,
+            "span_walker_full_packet_32_quads_1920x1080_ms": float(np.median(sw_ms)), "span_walker_cpu_port_ms": sw_cpu_ms,
+            "span_walker_matches_oracle": same18, "span_walker_launches": 5,
+            "macrotile_frame_1280x720_vd12_e2e_ms": float(np.median(mt_ms)), "macrotile_meshes": int(ids18.size),
+            "note": "vx_span_walk_quads_device (benches/span_walker.rs:36-77 workload, framebuffer resident) and vx_render_frame with cfg.macrotile = 1 (render_frame_macrotile) through the host API into mapped host memory, wall clock"}
 
 
 _REAL_STDOUT_FD = None
@@ -813,10 +964,30 @@ def main():
     return run_cuda(args)
 
 
-if __name__ == "__main__":
-    rc = main()
-    # Leave without interpreter-exit destructors: torch frees cached device / page-locked tensors after the CUDA context
-    # is already gone there and aborts the process (exit code 134) although the run has completed.
+def leave(rc: int):
+    """Exit-time hooks first (the driver's loaded-library report among them), then leave without running static
+    destructors: at that point torch would free cached device / page-locked blocks after the CUDA context is gone and abort a
+    run that has completed."""
+    import atexit
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(int(rc or 0))
+    try:
+        atexit._run_exitfuncs()
+    except Exception as e:  # noqa: BLE001
+        print("exit hook raised:", repr(e), file=sys.stderr)
+        rc = rc or 1
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(int(rc))
+
+
+if __name__ == "__main__":
+    try:
+        _rc = main()
+    except SystemExit as e:
+        _rc = int(e.code or 0)
+    except BaseException:  # noqa: BLE001
+        import traceback
+        traceback.print_exc()
+        _rc = 1
+    leave(int(_rc or 0))

@@ -65,6 +65,12 @@ class VxMeshBatchDevice(C.Structure):
                 ("d_positions", C.c_void_p)]
 
 
+class VxShardLayout(C.Structure):
+    _fields_ = [("rank_stride", C.c_int64), ("off_quad_base", C.c_int64), ("off_quad_count", C.c_int64),
+                ("off_slice_offsets", C.c_int64), ("off_face_aabb", C.c_int64), ("off_has_mesh", C.c_int64),
+                ("off_quads", C.c_int64), ("quads_capacity", C.c_int64), ("rows_per_rank", C.c_int32), ("reserved", C.c_int32)]
+
+
 class VxFrameStats(C.Structure):
     _fields_ = [("n_input", C.c_int32), ("n_survivors", C.c_int32), ("n_quads", C.c_int32),
                 ("n_triangles", C.c_int32), ("n_bin_entries", C.c_int32), ("n_kernel_launches", C.c_int32),
@@ -84,6 +90,17 @@ PROTOTYPES = {
     "vx_context_launch_count": (C.c_int64, [_P]),
     "vx_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "vx_host_free": (None, [_P, _P]),
+    "vx_device_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    "vx_device_free": (C.c_int, [_P, _P]),
+    "vx_ipc_export": (C.c_int, [_P, _P, _P]),
+    "vx_ipc_open": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "vx_ipc_close": (C.c_int, [_P, _P]),
+    "vx_signal_flags": (C.c_int, [_P, _P, _I, C.c_uint32]),
+    "vx_wait_flags": (C.c_int, [_P, _P, _I, _I, C.c_uint32, _I]),
+    "vx_wait_status": (C.c_int, [_P, C.POINTER(_I)]),
+    "vx_shard_layout": (C.c_int, [_I, C.c_int64, C.POINTER(VxShardLayout)]),
+    "vx_mesh_shard_pack": (C.c_int, [_P, _P, C.POINTER(VxShardLayout), _P]),
+    "vx_mesh_batch_assemble_shards": (C.c_int, [_P, _I, _I, _P, C.POINTER(VxShardLayout), _P, _P, C.POINTER(_P)]),
     "vx_generate_terrain": (C.c_int, [_P, _P, _I, C.POINTER(VxTerrainParams), _P, _P]),
     "vx_mesh_chunks": (C.c_int, [_P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
     "vx_mesh_batch_update": (C.c_int, [_P, _P, _P, _I, _P, _P, C.POINTER(_I)]),
@@ -114,6 +131,8 @@ PROTOTYPES = {
     "vx_span_walk_quads_device": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "vx_fill_spans": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "vx_hyper_pipeline_render": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _P, _P, C.POINTER(_I)]),
+    "vx_render_frame_begin": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig), _P, _P, C.POINTER(_I)]),
+    "vx_render_frame_end": (C.c_int, [_P, _I, _P, C.POINTER(_I)]),
     "vx_render_frame_device": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig)]),
     "vx_render_frame_into": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig), _P, _P]),
     "vx_framebuffer_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I), C.POINTER(_I)]),

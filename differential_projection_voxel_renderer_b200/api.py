@@ -572,6 +572,44 @@ class FrameLoop:
             self.ctx.check(rc)
         return self.color, self.depth, self.survivors[:self._ns.value]
 
+    # ---- pipelined use (vx_render_frame_begin / _end): frame k + 1 is enqueued before the host waits for frame k, the
+    #      way main.rs:320-336 presents one frame while the next loop iteration is already running -------------------------
+    def _second_set(self):
+        if getattr(self, "_sets", None) is None:
+            rows = self.color.shape[0]
+            color2 = self.ctx.host_array((rows, self.cfg.width), np.uint32)
+            depth2 = self.ctx.host_array((rows, self.cfg.width), np.float32) if self.depth is not None else None
+            self._sets = [(self.color, self.depth, self.survivors), (color2, depth2, np.empty_like(self.survivors))]
+            self._ticket = C.c_int32(0)
+            self._set_of = [0, 1]  # buffer set used by the in-flight frame with ticket parity 0 / 1
+        return self._sets
+
+    def submit(self, view_proj, camera_position) -> int:
+        """Enqueue one frame without waiting for it; returns its ticket.  At most two frames may be in flight."""
+        sets = self._second_set()
+        self._vp[:] = np.asarray(view_proj, dtype=np.float32).reshape(16)
+        self._cam[:] = camera_position
+        lib, a = self.ctx.lib, self._args
+        k = getattr(self, "_n_submitted", 0)
+        color, depth, _ = sets[k & 1]
+        rc = lib.vx_render_frame_begin(a[0], a[1], None, -1, a[4], a[5], a[6], a[7], color.ctypes.data,
+                                       depth.ctypes.data if depth is not None else None, C.byref(self._ticket))
+        if rc != 0:
+            self.ctx.check(rc)
+        self._n_submitted = k + 1
+        self._set_of[int(self._ticket.value) & 1] = k & 1
+        return int(self._ticket.value)
+
+    def wait(self, ticket: int):
+        """Block until the frame `ticket` is complete in host memory: returns (color, depth or None, survivors) -- views
+        that stay valid until the frame after the next one is submitted."""
+        sets = self._second_set()
+        color, depth, surv = sets[self._set_of[ticket & 1]]
+        rc = self.ctx.lib.vx_render_frame_end(self.ctx.handle, int(ticket), surv.ctypes.data, C.byref(self._ns))
+        if rc != 0:
+            self.ctx.check(rc)
+        return color, depth, surv[:self._ns.value]
+
 
 def render_frame_device(batch: MeshBatch, view_proj, camera_position, cfg: VxFrameConfig, view_distance: int,
                         ctx: Optional[Context] = None):

@@ -83,6 +83,10 @@ struct VxContext {
     // small reusable staging buffers
     VxDeviceBuffer tmp_a, tmp_b, tmp_c, tmp_d;
     VxPinnedBuffer pinned;
+    // vx_multi.cu: device copy of the last flag-pointer table, status word of the wait kernel
+    VxDeviceBuffer multi_ptrs, multi_status;
+    uint32_t *multi_ptrs_host[32] = {};
+    int multi_ptrs_n = 0;
 };
 
 inline int vx_fail(VxContext *ctx, int code, const char *msg) {

@@ -37,6 +37,8 @@ void vx_context_destroy(VxContext *ctx) {
     ctx->tmp_c.release();
     ctx->tmp_d.release();
     ctx->pinned.release();
+    ctx->multi_ptrs.release();
+    ctx->multi_status.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

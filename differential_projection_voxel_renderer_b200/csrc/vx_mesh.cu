@@ -541,6 +541,36 @@ int run_mesher(VxContext *ctx, const uint8_t *d_vox, const int32_t *d_nb, const 
     return vx_fail(ctx, VX_ERR_CAPACITY, "mesher output did not fit after regrow");
 }
 
+struct ShardOffsets {
+    uint32_t off[64]; // first quad of rank r's stream in the assembled stream
+};
+
+// one CTA per chunk of the assembled batch: copy its row from the gathered shard blocks (vx_mesh_batch_assemble_shards)
+__global__ void __launch_bounds__(64) assemble_shards_kernel(int n_chunks, int world, ShardOffsets so, const uint8_t *__restrict__ blocks, VxShardLayout L,
+                                                             uint32_t *quad_base, uint32_t *quad_count, uint32_t *slice_offsets, int32_t *face_aabb,
+                                                             uint8_t *has_mesh, unsigned long long *cursor, unsigned long long total) {
+    const int c = blockIdx.x;
+    if (c >= n_chunks) return;
+    const int r = c % world;
+    const size_t j = (size_t)(c / world);
+    const uint8_t *blk = blocks + (size_t)r * (size_t)L.rank_stride;
+    const uint32_t *g_base = reinterpret_cast<const uint32_t *>(blk + L.off_quad_base), *g_count = reinterpret_cast<const uint32_t *>(blk + L.off_quad_count);
+    const uint32_t *g_so = reinterpret_cast<const uint32_t *>(blk + L.off_slice_offsets);
+    const int32_t *g_aabb = reinterpret_cast<const int32_t *>(blk + L.off_face_aabb);
+    const uint8_t *g_has = blk + L.off_has_mesh;
+    for (int i = threadIdx.x; i < 198; i += 64) slice_offsets[(size_t)c * 198 + i] = g_so[j * 198 + i];
+    if (threadIdx.x < 36) face_aabb[(size_t)c * 36 + threadIdx.x] = g_aabb[j * 36 + threadIdx.x];
+    if (threadIdx.x == 36) quad_base[c] = g_base[j] + so.off[r];
+    if (threadIdx.x == 37) quad_count[c] = g_count[j];
+    if (threadIdx.x == 38) has_mesh[c] = g_has[j];
+    if (c == 0 && threadIdx.x == 39) {
+        cursor[0] = total;
+        cursor[1] = 0;
+        cursor[2] = 0;
+        cursor[3] = 0;
+    }
+}
+
 // one CTA per live chunk: move its quads from the old stream to their place in the compacted one
 __global__ void __launch_bounds__(256) compact_quads_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const uint4 *__restrict__ moves, int n_moves) {
     for (int m = blockIdx.x; m < n_moves; m += gridDim.x) {
@@ -904,6 +934,102 @@ int vx_mesh_batch_upload(VxContext *ctx, const uint8_t *quads, int64_t total_qua
     b->total_quads = total_quads;
     b->n_meshes = nm;
     *out = b;
+    return VX_OK;
+}
+
+// Chunk-sharded meshing, exchange step (binary_greedy.rs:62-78 returns every mesh to the caller): rank r
+// meshed the chunks k with k % world == r into a compact shard batch (row j = chunk r + j * world).  Each rank packs
+// its shard into one block (vx_mesh_shard_pack), the blocks are all-gathered (one NCCL collective), and
+// vx_mesh_batch_assemble_shards puts them back into one batch in chunk order.  The quad stream is the concatenation
+// of the shards' streams (a chunk's quads stay contiguous and in reference order; only quad_base is rebased), so no
+// quad is touched more than once.
+int vx_shard_layout(int32_t rows_per_rank, int64_t max_shard_quads, VxShardLayout *out) {
+    if (!out || rows_per_rank < 0 || max_shard_quads < 0) return VX_ERR_INVALID;
+    auto up16 = [](int64_t v) { return (v + 15) & ~(int64_t)15; };
+    const int64_t rows = rows_per_rank;
+    int64_t o = 0;
+    out->rows_per_rank = rows_per_rank;
+    out->off_quad_base = o; o = up16(o + 4 * rows);
+    out->off_quad_count = o; o = up16(o + 4 * rows);
+    out->off_slice_offsets = o; o = up16(o + 4 * 198 * rows);
+    out->off_face_aabb = o; o = up16(o + 4 * 36 * rows);
+    out->off_has_mesh = o; o = up16(o + rows);
+    out->off_quads = o; o = up16(o + 3 * max_shard_quads);
+    out->quads_capacity = max_shard_quads;
+    out->rank_stride = o;
+    return VX_OK;
+}
+
+int vx_mesh_shard_pack(VxContext *ctx, const VxMeshBatch *shard, const VxShardLayout *L, uint8_t *d_block) {
+    if (!ctx || !shard || !L || !d_block || shard->n_chunks > L->rows_per_rank) return vx_fail(ctx, VX_ERR_INVALID, "vx_mesh_shard_pack: bad argument");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    VxMeshBatchInfo info;
+    int rc = vx_mesh_batch_info(ctx, shard, &info);
+    if (rc != VX_OK) return rc;
+    if (info.total_quads > L->quads_capacity) return vx_fail(ctx, VX_ERR_CAPACITY, "shard has more quads than the layout holds");
+    const size_t n = (size_t)shard->n_chunks;
+    auto cp = [&](int64_t off, const void *src, size_t bytes) -> cudaError_t {
+        return bytes ? cudaMemcpyAsync(d_block + off, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream) : cudaSuccess;
+    };
+    VX_CUDA(ctx, cp(L->off_quad_base, shard->quad_base.ptr, 4 * n));
+    VX_CUDA(ctx, cp(L->off_quad_count, shard->quad_count.ptr, 4 * n));
+    VX_CUDA(ctx, cp(L->off_slice_offsets, shard->slice_offsets.ptr, 4 * 198 * n));
+    VX_CUDA(ctx, cp(L->off_face_aabb, shard->face_aabb.ptr, 4 * 36 * n));
+    VX_CUDA(ctx, cp(L->off_has_mesh, shard->has_mesh.ptr, n));
+    VX_CUDA(ctx, cp(L->off_quads, shard->quads.ptr, 3 * (size_t)info.total_quads));
+    return VX_OK;
+}
+
+int vx_mesh_batch_assemble_shards(VxContext *ctx, int32_t n_chunks, int32_t world, const uint8_t *d_blocks, const VxShardLayout *L,
+                                  const int64_t *shard_quads, const int32_t *d_positions, VxMeshBatch **batch_inout) {
+    if (!ctx || !batch_inout || !L || n_chunks < 0 || world < 1 || world > 64 || !shard_quads || (int64_t)L->rows_per_rank * world < n_chunks ||
+        (n_chunks > 0 && !d_blocks))
+        return vx_fail(ctx, VX_ERR_INVALID, "vx_mesh_batch_assemble_shards: bad argument");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t total = 0;
+    ShardOffsets so;
+    memset(&so, 0, sizeof(so));
+    for (int r = 0; r < world; ++r) {
+        if (shard_quads[r] < 0 || shard_quads[r] > L->quads_capacity) return vx_fail(ctx, VX_ERR_INVALID, "shard quad count exceeds the layout");
+        so.off[r] = (uint32_t)total;
+        total += shard_quads[r];
+    }
+    if (total >= (int64_t)1 << 32) return vx_fail(ctx, VX_ERR_CAPACITY, "more than 2^32 quads in one batch");
+    VxMeshBatch *b = *batch_inout;
+    const bool fresh = b == nullptr;
+    if (!fresh && b->n_chunks != n_chunks) return vx_fail(ctx, VX_ERR_INVALID, "batch was created for another chunk count");
+    if (fresh) {
+        b = new VxMeshBatch();
+        int rc = batch_alloc(ctx, b, n_chunks, total > 0 ? total + total / 8 : 1);
+        if (rc != VX_OK) { vx_mesh_batch_release(ctx, b); return rc; }
+    } else if (total > b->cap_quads) {
+        VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        VX_CUDA(ctx, b->quads.reserve(3 * (size_t)(total + total / 8) + 16));
+        b->cap_quads = total + total / 8;
+    }
+    cudaError_t e = cudaSuccess;
+    if (n_chunks > 0) {
+        if (d_positions) e = cudaMemcpyAsync(b->positions.ptr, d_positions, sizeof(int32_t) * 3 * (size_t)n_chunks, cudaMemcpyDeviceToDevice, ctx->stream);
+        else if (fresh) e = cudaMemsetAsync(b->positions.ptr, 0, sizeof(int32_t) * 3 * (size_t)n_chunks, ctx->stream);
+        if (e == cudaSuccess) {
+            assemble_shards_kernel<<<n_chunks, 64, 0, ctx->stream>>>(n_chunks, world, so, d_blocks, *L, b->quad_base.as<uint32_t>(), b->quad_count.as<uint32_t>(),
+                                                                     b->slice_offsets.as<uint32_t>(), b->face_aabb.as<int32_t>(), b->has_mesh.as<uint8_t>(),
+                                                                     b->cursor.as<unsigned long long>(), (unsigned long long)total);
+            ctx->launches++;
+            e = cudaGetLastError();
+        }
+    }
+    for (int r = 0; r < world && e == cudaSuccess; ++r)
+        if (shard_quads[r])
+            e = cudaMemcpyAsync(b->quads.as<uint8_t>() + 3 * (size_t)so.off[r], d_blocks + (size_t)r * (size_t)L->rank_stride + L->off_quads,
+                                3 * (size_t)shard_quads[r], cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        if (fresh) vx_mesh_batch_release(ctx, b);
+        return vx_cuda_fail(ctx, e, "assemble shards", __FILE__, __LINE__);
+    }
+    b->total_quads = total;
+    b->n_meshes = -1; // counted on demand (vx_mesh_batch_info)
+    *batch_inout = b;
     return VX_OK;
 }
 

@@ -156,6 +156,29 @@ VX_API int64_t vx_context_launch_count(const VxContext *ctx);
 VX_API int vx_host_alloc(VxContext *ctx, size_t bytes, void **out);
 VX_API void vx_host_free(VxContext *ctx, void *p);
 
+/* ---- one process per GPU: peer-mapped buffers and cross-GPU hand-off flags ----------------------------------
+ * The reference gives each Rayon worker a disjoint `&mut` stripe of ONE framebuffer (framebuffer.rs:392-431,
+ * main.rs:581-597).  Across GPUs the composed frame lives in one GPU's memory; the other processes map it with CUDA
+ * IPC and pass the mapped pointer (offset to their stripe's first row) to vx_render_frame_into, so the raster kernel's
+ * write-out stores the stripe over NVLink -- no staging copy and no collective.  Per frame only a 32-bit counter per
+ * rank crosses the link:
+ *   vx_device_alloc / vx_device_free   zero-filled device memory with its own allocation (exportable)
+ *   vx_ipc_export / vx_ipc_open / vx_ipc_close   64-byte handle of such an allocation / mapping in another process
+ *   vx_signal_flags  enqueue on ctx's stream: after everything already enqueued has completed, publish `value` into
+ *                    each of the n (<= 32) flag words (d_flags = HOST array of n device addresses, local or
+ *                    peer-mapped), release semantics at system scope
+ *   vx_wait_flags    enqueue: one warp polls n flag words of THIS GPU (`stride_words` apart) until all have reached
+ *                    `value` (wrap-safe >=), or timeout_us (<= 0: 2 s) passes -- then the status is set, nothing hangs
+ *   vx_wait_status   synchronises the stream; VX_ERR_CUDA + *timed_out = 1 if a wait since the last call timed out */
+VX_API int vx_device_alloc(VxContext *ctx, size_t bytes, void **d_out);
+VX_API int vx_device_free(VxContext *ctx, void *d_ptr);
+VX_API int vx_ipc_export(VxContext *ctx, void *d_ptr, uint8_t handle_out[64]);
+VX_API int vx_ipc_open(VxContext *ctx, const uint8_t handle[64], void **d_out);
+VX_API int vx_ipc_close(VxContext *ctx, void *d_ptr);
+VX_API int vx_signal_flags(VxContext *ctx, uint32_t *const *d_flags, int32_t n, uint32_t value);
+VX_API int vx_wait_flags(VxContext *ctx, const uint32_t *d_flags, int32_t n, int32_t stride_words, uint32_t value, int32_t timeout_us);
+VX_API int vx_wait_status(VxContext *ctx, int32_t *timed_out);
+
 /* ---- terrain generation (the step before meshing) -------------------- */
 
 /* Improved 2-D gradient noise tables + the constants of chunk.rs:173-177 (scale 0.01, amplitude 20). */
@@ -244,6 +267,26 @@ VX_API int vx_mesh_batch_download(VxContext *ctx, const VxMeshBatch *b, uint8_t 
 VX_API int vx_mesh_batch_upload(VxContext *ctx, const uint8_t *quads, int64_t total_quads, const uint32_t *quad_base,
                          const uint32_t *quad_count, const uint32_t *slice_offsets, const int32_t *face_aabb,
                          const uint8_t *has_mesh, const int32_t *positions, int32_t n_chunks, VxMeshBatch **out);
+/* Chunk-sharded meshing across GPUs, exchange step (BinaryGreedyMesher::mesh_world returns EVERY mesh to its caller,
+ * binary_greedy.rs:62-78): rank r meshes the chunks k with k % world == r (vx_mesh_chunk_subset_device; row j of the
+ * shard = chunk r + j * world).  vx_shard_layout fixes one block layout for all ranks (sections quad_base / quad_count /
+ * slice_offsets / face_aabb / has_mesh / quad stream, 16-byte aligned; host-only helper), vx_mesh_shard_pack copies a
+ * shard into its block, the caller all-gathers the blocks (one NCCL collective over NVLink; rank r's block at
+ * d_blocks + r * rank_stride) and vx_mesh_batch_assemble_shards builds the batch in chunk order on every rank:
+ * shard_quads[r] (host) = quads in rank r's stream.  The assembled quad stream is the concatenation of the shard
+ * streams; per-chunk quad lists stay bit-identical.  *batch_inout NULL: a new batch; else re-filled in place. */
+typedef struct {
+    int64_t rank_stride;  /* bytes per block */
+    int64_t off_quad_base, off_quad_count, off_slice_offsets, off_face_aabb, off_has_mesh, off_quads;
+    int64_t quads_capacity; /* quads a block's stream section holds */
+    int32_t rows_per_rank;  /* ceil(n_chunks / world) */
+    int32_t reserved;
+} VxShardLayout;
+VX_API int vx_shard_layout(int32_t rows_per_rank, int64_t max_shard_quads, VxShardLayout *out);
+VX_API int vx_mesh_shard_pack(VxContext *ctx, const VxMeshBatch *shard, const VxShardLayout *layout, uint8_t *d_block);
+VX_API int vx_mesh_batch_assemble_shards(VxContext *ctx, int32_t n_chunks, int32_t world, const uint8_t *d_blocks,
+                                  const VxShardLayout *layout, const int64_t *shard_quads, const int32_t *d_positions,
+                                  VxMeshBatch **batch_inout);
 VX_API void vx_mesh_batch_release(VxContext *ctx, VxMeshBatch *b);
 
 /* BinaryGreedyMesher::greedy_mesh_slice (binary_greedy.rs:675) for n_slices masks of 32 rows.
@@ -288,6 +331,17 @@ VX_API int vx_set_atlas(VxContext *ctx, const VxAtlas *atlas);
 VX_API int vx_render_frame(VxContext *ctx, const VxMeshBatch *batch, const int32_t *mesh_ids, int32_t n_meshes,
                     const float vp[16], const float cam_pos[3], int32_t view_distance, const VxFrameConfig *cfg,
                     uint32_t *color_out, float *depth_out, int32_t *survivors_out, int32_t *n_survivors);
+/* Pipelined vx_render_frame: the reference's loop presents frame k while the next iteration is already under way
+ * (main.rs:320-336).  _begin enqueues one whole frame -- draw-list upload, cull / setup / raster, read-back of the
+ * statistics and the draw order -- and returns a ticket without waiting for the GPU; _end(ticket) blocks until THAT
+ * frame is complete in color_out / depth_out and hands out its draw order.  At most two frames are in flight
+ * (begin k+1 may precede end k), so each needs its own buffers, and the buffers must be device-mapped page-locked
+ * memory (vx_host_alloc): the raster kernel writes them in place.  A frame whose scratch overflowed is re-rendered
+ * synchronously inside _end, so the result is always the same as vx_render_frame's. */
+VX_API int vx_render_frame_begin(VxContext *ctx, const VxMeshBatch *batch, const int32_t *mesh_ids, int32_t n_meshes,
+                          const float vp[16], const float cam_pos[3], int32_t view_distance, const VxFrameConfig *cfg,
+                          uint32_t *color_out, float *depth_out, int32_t *ticket);
+VX_API int vx_render_frame_end(VxContext *ctx, int32_t ticket, int32_t *survivors_out, int32_t *n_survivors);
 /* Device-resident variant: nothing is copied back; the frame stays in the context's framebuffer
  * (see vx_framebuffer_device).  Used with CUDA-event timing and for multi-GPU composition. */
 VX_API int vx_render_frame_device(VxContext *ctx, const VxMeshBatch *batch, const int32_t *d_mesh_ids, int32_t n_meshes,

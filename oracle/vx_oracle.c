@@ -174,7 +174,7 @@ static void generate_binary_masks(const uint8_t *c, const uint8_t *nb, int nb_un
 /* mesh_chunk_in_world binary_greedy.rs:83-121 + mesh_face :213-264 +
  * ChunkMesh::add_quad mesh.rs:489-523 + FaceList::add_quad mesh.rs:369-397. */
 int vxo_mesh_chunk(const uint8_t *voxels, const uint8_t *const nbr_voxels[6], const int32_t nbr_code[6],
-                   uint8_t *quads_out, int cap, uint32_t *slice_offsets, int32_t *face_aabb) {
+                   uint8_t *quads_out, int cap, uint32_t slice_offsets[6 * 33], int32_t face_aabb[6 * 6]) {
     int n = 0;
     uint32_t masks[4][CS];
     int used[4];
@@ -506,6 +506,14 @@ static int clip_triangle_near_textured(const clip_vtx tri[3], float threshold, c
     return 0;
 }
 
+#ifdef VXO_STATS
+/* workload statistics (tools/frame_stats_cpu.py builds a separate library with -DVXO_STATS; single-threaded use) */
+uint64_t vxo_stats[64]; /* 0 triangles setup, 1 rows visited, 2 spans, 3 fragments, 4 depth passes, 8.. span length histogram (log2) */
+#define VXO_STAT(i, n) (vxo_stats[i] += (uint64_t)(n))
+#else
+#define VXO_STAT(i, n) ((void)0)
+#endif
+
 /* rasterizer.rs:1219-1467 */
 static void render_triangle_span_from_clip(const clip_vtx tri_in[3], int block_type, float light, target_t *tg) {
     const float NEAR_W_EPS = 0.001f; /* rasterizer.rs:18 */
@@ -553,8 +561,10 @@ static void render_triangle_span_from_clip(const clip_vtx tri_in[3], int block_t
 
         int y_start = f2i(floorf(min_y));
         int y_end = f2i(ceilf(max_y));
+        VXO_STAT(0, 1);
         for (int y = y_start; y <= y_end; ++y) {
             if (y < rect_y0 || y >= f2i(rect_y_limit)) continue;
+            VXO_STAT(1, 1);
             float y_center = (float)y + 0.5f;
             span_vtx pts[2] = {vs[0], vs[0]};
             int count = 0;
@@ -599,6 +609,16 @@ static void render_triangle_span_from_clip(const clip_vtx tri_in[3], int block_t
             float step_u = (pts[1].u_over_w - pts[0].u_over_w) * inv_span;
             float step_v = (pts[1].v_over_w - pts[0].v_over_w) * inv_span;
             float step_w = (pts[1].inv_w - pts[0].inv_w) * inv_span;
+#ifdef VXO_STATS
+            {
+                int len = x_end - x_start + 1, lg = 0;
+                while ((1 << (lg + 1)) <= len) lg++;
+                VXO_STAT(2, 1);
+                VXO_STAT(3, len);
+                VXO_STAT(8 + lg, 1);
+                VXO_STAT(24 + lg, len);
+            }
+#endif
 
             for (int x = x_start; x <= x_end; ++x) {
                 /* FrameSlice::test_depth_and_get_index framebuffer.rs:30-51.  The reference
@@ -607,6 +627,7 @@ static void render_triangle_span_from_clip(const clip_vtx tri_in[3], int block_t
                  * (x_end = floor(min(.., W) - 0.5) <= W - 1). */
                 size_t idx = (size_t)y * (size_t)tg->W + (size_t)x;
                 if (z_val < tg->depth[idx]) {
+                    VXO_STAT(4, 1);
                     tg->depth[idx] = z_val;
                     float u = u_over_w / inv_w;
                     float v = v_over_w / inv_w;

@@ -211,6 +211,59 @@ def test_stripe_frames_compose_to_the_full_frame(ctx, ob, scene5):
         assert np.array_equal(np.concatenate(parts_d).view(np.uint32), od.view(np.uint32))
 
 
+def test_unequal_stripes_compose_and_report_the_full_draw_order(ctx, ob, scene5):
+    """Work-balanced (unequal) stripes: a survivor whose screen rect misses a stripe is not projected or binned there
+    (main.rs:528-557) but keeps its place in the draw order; the stripes still concatenate to the full frame."""
+    _, p, batch, ref = scene5
+    w, h = 640, 360
+    for cam_i in (0, 1, 3):
+        cam = vx_scenes.path_camera(cam_i, w, h)
+        vp, ids, oc, od, osurv = oracle_frame(ob, ref, p, cam, w, h, 5)
+        for cuts in ((0, 8, 200, 208, 360), (0, 176, 184, 192, 360), (0, 359, 360)):
+            parts_c, parts_d = [], []
+            for y0, y1 in zip(cuts[:-1], cuts[1:]):
+                cfg = api.default_frame_config(w, h)
+                cfg.stripe_y0, cfg.stripe_rows = y0, y1 - y0
+                c, d, surv = api.render_frame(batch, vp, cam.position, cfg, mesh_ids=ids, ctx=ctx)
+                assert np.array_equal(surv, osurv)
+                parts_c.append(c); parts_d.append(d)
+            assert np.array_equal(np.concatenate(parts_c), oc)
+            assert np.array_equal(np.concatenate(parts_d).view(np.uint32), od.view(np.uint32))
+
+
+def test_pipelined_frame_loop_two_frames_in_flight(ctx, ob, scene5):
+    """vx_render_frame_begin / _end through api.FrameLoop.submit / wait: frame k + 1 is enqueued before frame k is
+    waited for; every frame (colour, depth, draw order) equals the oracle's for ITS camera."""
+    _, p, batch, ref = scene5
+    w, h = 640, 360
+    cfg = api.default_frame_config(w, h)
+    loop = api.FrameLoop(batch, cfg, view_distance=5, want_depth=True, ctx=ctx)
+    cams = [vx_scenes.path_camera(k % len(vx_scenes.CAMERA_PATH), w, h) for k in range(7)]
+    want = [oracle_frame(ob, ref, p, c, w, h, 5) for c in cams]
+    tickets = []
+    for k, cam in enumerate(cams):
+        tickets.append(loop.submit(cam.view_projection(), cam.position))
+        if k >= 1:
+            color, depth, surv = loop.wait(tickets[k - 1])
+            _, _, oc, od, osurv = want[k - 1]
+            assert np.array_equal(surv, osurv)
+            assert np.array_equal(color, oc) and np.array_equal(depth.view(np.uint32), od.view(np.uint32))
+    color, depth, surv = loop.wait(tickets[-1])
+    _, _, oc, od, osurv = want[-1]
+    assert np.array_equal(surv, osurv) and np.array_equal(color, oc) and np.array_equal(depth.view(np.uint32), od.view(np.uint32))
+    # a third frame in flight is refused, an unknown ticket too; the synchronous call still works afterwards
+    t0 = loop.submit(cams[0].view_projection(), cams[0].position)
+    t1 = loop.submit(cams[1].view_projection(), cams[1].position)
+    with pytest.raises(api.VxError):
+        loop.submit(cams[2].view_projection(), cams[2].position)
+    loop.wait(t0)
+    loop.wait(t1)
+    with pytest.raises(api.VxError):
+        loop.wait(t1)
+    color, depth, surv = loop.render(cams[2].view_projection(), cams[2].position)
+    assert np.array_equal(color, want[2][2])
+
+
 def test_empty_and_degenerate_inputs(ctx, ob, scene5):
     _, p, batch, ref = scene5
     cfg = api.default_frame_config(64, 48)
