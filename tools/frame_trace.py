@@ -43,13 +43,25 @@ for lo, hi in ((0, 0), (1, 8), (9, 64), (65, 255), (256, 100000)):
         print(f"  n_src {lo:4d}..{hi:<6d}: {int(m.sum()):5d} items  mean {dur[m].mean():6.2f}  max {dur[m].max():6.2f} us")
 ph = t[:, 6:9] - t[:, 2:3]
 m = nsrc > 0
-print("phase ends after item start (us, items with work): keys %.2f  expansion %.2f  first task round %.2f  end %.2f" % tuple(
+print("phase ends after item start (us, items with work): keys ready %.2f  warp 0 out of work %.2f  all warps done %.2f  end %.2f" % tuple(
     [float(np.mean(ph[m, k])) / 1000 for k in range(3)] + [float(dur[m].mean())]))
-cyc = t[:, 9:13].astype(np.float64)
-mm = m & (cyc[:, 3] > 0)
-print("thread-0 first task (cycles, mean over %d items): load %.0f  edges %.0f  span+jump %.0f  pixels %.0f  npix %.1f" % (
-    int(mm.sum()), cyc[mm, 0].mean(), cyc[mm, 1].mean(), cyc[mm, 2].mean(), cyc[mm, 3].mean(), t[mm, 13].mean()))
+pp = t[:, 10:13]
+rounds = t[:, 13]
+mm2 = m & (pp[:, 0] > 0) & (t[:, 9] > 0)
+if mm2.any():
+    print("first round (single-part items): phase P starts %.2f  warp 0 done with P %.2f  second round starts %.2f us after item start; rounds mean %.2f max %d" % (
+        float(np.mean(pp[mm2, 0] - t0[mm2])) / 1000, float(np.mean(pp[mm2, 1] - t0[mm2])) / 1000,
+        float(np.mean(np.where(pp[mm2, 2] > 0, pp[mm2, 2] - t0[mm2], 0))) / 1000, float(rounds[mm2].mean()), int(rounds[mm2].max())))
+wo = t[:, 9]
+mm = m & (wo > 0)
+if mm.any():
+    print("single-part items: write-out starts %.2f us after item start, takes %.2f us (mean over %d items)" % (
+        float(np.mean(wo[mm] - t0[mm])) / 1000, float(np.mean(t1[mm] - wo[mm])) / 1000, int(mm.sum())))
 order = np.argsort(-dur)[:12]
+for i in order[:6]:
+    rel = lambda v: (v - t0[i]) / 1000.0 if v > 0 else float("nan")
+    print(f"  slow item {i} phases (us after start): keys {rel(t[i, 6]):.2f} | R0 warp0 done {rel(t[i, 7]):.2f} | P0 starts {rel(pp[i, 0]):.2f} | P0 warp0 done {rel(pp[i, 1]):.2f} | round 2 starts {rel(pp[i, 2]):.2f} | "
+          f"all rounds done {rel(t[i, 8]):.2f} | write-out starts {rel(t[i, 9]):.2f} | end {dur[i]:.2f} | rounds {rounds[i]}")
 for i in order:
     print(f"  slow: item {i} tile ({tile[i] % ((W + 127) // 128)},{tile[i] // ((W + 127) // 128)}) part {part[i]}/{parts[i]} n_src {nsrc[i]} dur {dur[i]:.1f} us start {(t0[i] - base) / 1000:.1f} sm {sm[i]}")
 late = np.argsort(-t1)[:8]
