@@ -75,6 +75,7 @@ struct VxContext {
     int device = 0;
     int num_sms = VX_NUM_SMS_B200;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // device -> host frame transfers of the pipelined frame path (created on first use)
     int64_t launches = 0;
     std::string last_error;
     VxAtlas atlas;

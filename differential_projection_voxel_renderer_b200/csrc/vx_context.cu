@@ -31,6 +31,7 @@ void vx_context_destroy(VxContext *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     vx_frame_scratch_destroy(ctx);
     ctx->tmp_a.release();
     ctx->tmp_b.release();
@@ -39,6 +40,10 @@ void vx_context_destroy(VxContext *ctx) {
     ctx->pinned.release();
     ctx->multi_ptrs.release();
     ctx->multi_status.release();
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

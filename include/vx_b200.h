@@ -335,9 +335,11 @@ VX_API int vx_render_frame(VxContext *ctx, const VxMeshBatch *batch, const int32
  * (main.rs:320-336).  _begin enqueues one whole frame -- draw-list upload, cull / setup / raster, read-back of the
  * statistics and the draw order -- and returns a ticket without waiting for the GPU; _end(ticket) blocks until THAT
  * frame is complete in color_out / depth_out and hands out its draw order.  At most two frames are in flight
- * (begin k+1 may precede end k), so each needs its own buffers, and the buffers must be device-mapped page-locked
- * memory (vx_host_alloc): the raster kernel writes them in place.  A frame whose scratch overflowed is re-rendered
- * synchronously inside _end, so the result is always the same as vx_render_frame's. */
+ * (begin k+1 may precede end k), so each needs its own buffers, and the buffers must be page-locked memory
+ * (vx_host_alloc): the frame is rendered into a device buffer of its in-flight slot and leaves through the copy engine
+ * on a second stream, so the PCIe transfer of frame k runs beside the kernels of frame k+1 (steady-state period =
+ * max(render, transfer)).  A frame whose scratch overflowed is re-rendered synchronously inside _end, so the result
+ * is always the same as vx_render_frame's. */
 VX_API int vx_render_frame_begin(VxContext *ctx, const VxMeshBatch *batch, const int32_t *mesh_ids, int32_t n_meshes,
                           const float vp[16], const float cam_pos[3], int32_t view_distance, const VxFrameConfig *cfg,
                           uint32_t *color_out, float *depth_out, int32_t *ticket);
