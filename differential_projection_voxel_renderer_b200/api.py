@@ -230,7 +230,8 @@ def upload_mesh_batch(ctx: Context, quads, quad_base, quad_count, slice_offsets,
 
 
 def terrain_params(seed: int = 12345) -> VxTerrainParams:
-    """Noise tables of the host generator (worldgen.py) + chunk.rs:173-177 constants."""
+    """noise 0.9.0 Perlin::new(seed) tables (permutation table doubled, the four diagonal gradients twice) +
+    chunk.rs:173-177 constants."""
     from . import worldgen
     tp = VxTerrainParams()
     perm = worldgen._perm_table(seed)

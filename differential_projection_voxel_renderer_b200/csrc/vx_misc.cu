@@ -263,12 +263,12 @@ __global__ void __launch_bounds__(HZ_THREADS) horizon_cull_kernel(HorizonArgs a)
 
 // ------------------------------------------------------------------------------------------------
 // Terrain generation (Chunk::generate_terrain, chunk.rs:114-207): heightfield
-// h = trunc(noise(x * scale, z * scale) * amplitude) from improved 2-D gradient noise in f64, Grass at y == h, Dirt
-// for h-3 < y < h, Stone below, Air above; chunks entirely above the terrain are Uniform(Air), chunks more than 10
-// below it Uniform(Stone) (chunk.rs:127-134).  One CTA per chunk.  The arithmetic follows worldgen.py operation by
-// operation (this translation unit is compiled -fmad=false), so the voxels equal the host generator's bit for bit.
-// The reference samples the `noise` crate, which is not available here: its exact heights are parity-unpinned
-// (DESIGN.md 5), the permutation / gradient tables are therefore inputs.
+// h = trunc(noise(x * scale, z * scale) * amplitude) with `noise 0.9.0` perlin_2d in f64 (restated in
+// the CPU test restatement (oracle/) from the crate's published source), Grass at y == h, Dirt for h-3 < y < h, Stone below, Air above;
+// chunks entirely above the terrain are Uniform(Air), chunks more than 10 below it Uniform(Stone) (chunk.rs:127-134).
+// One CTA per chunk.  The arithmetic follows the oracle operation by operation (this translation unit is compiled
+// -fmad=false), so the voxels equal the oracle's and the host generator's bit for bit.  The permutation table
+// (PermutationTable::new(seed)) and the four gradients are inputs.
 // ------------------------------------------------------------------------------------------------
 struct TerrainArgs {
     const int32_t *positions; // [n][3]
@@ -280,7 +280,10 @@ struct TerrainArgs {
     uint8_t *flags;           // [n]
 };
 
-__device__ __forceinline__ double terrain_fade(double t) { return t * t * t * (t * (t * 6.0 - 15.0) + 10.0); }
+__device__ __forceinline__ double terrain_fade(double t) { // map_quintic: clamp to [0, 1], then t^3 (t (6 t - 15) + 10)
+    const double x = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+    return x * x * x * (x * (x * 6.0 - 15.0) + 10.0);
+}
 
 __global__ void __launch_bounds__(256) generate_terrain_kernel(TerrainArgs a) {
     __shared__ int32_t h[32][32]; // [z][x]
@@ -296,20 +299,24 @@ __global__ void __launch_bounds__(256) generate_terrain_kernel(TerrainArgs a) {
         int mn = INT32_MAX, mx = INT32_MIN;
         for (int c = tid; c < 1024; c += 256) {
             const int lz = c >> 5, lx = c & 31;
+            // noise 0.9.0 perlin_2d (core/perlin.rs), restated in the CPU restatement under oracle/
             const double x = (double)(cx * VX_CHUNK_SIZE + lx) * a.scale;
             const double y = (double)(cz * VX_CHUNK_SIZE + lz) * a.scale;
             const double fx = floor(x), fy = floor(y);
             const long long xi0 = (long long)fx, yi0 = (long long)fy;
             const double xf = x - (double)xi0, yf = y - (double)yi0;
-            const int xi = (int)(xi0 & 255), yi = (int)(yi0 & 255);
-            const int aa = a.perm[a.perm[xi] + yi], ab = a.perm[a.perm[xi] + yi + 1];
-            const int ba = a.perm[a.perm[xi + 1] + yi], bb = a.perm[a.perm[xi + 1] + yi + 1];
+            double g[2][2];
+#pragma unroll
+            for (int ox = 0; ox < 2; ++ox)
+#pragma unroll
+                for (int oy = 0; oy < 2; ++oy) {
+                    const double qx = xf - (double)ox, qy = yf - (double)oy;
+                    const int hh = a.perm[a.perm[(int)((xi0 + ox) & 255)] ^ (int)((yi0 + oy) & 255)] & 3; // NoiseHasher::hash
+                    g[ox][oy] = a.grad[hh][0] * qx + a.grad[hh][1] * qy; // gradients are (+-1, +-1): exactly +-qx +- qy
+                }
             const double u = terrain_fade(xf), v = terrain_fade(yf);
-#define VX_GRAD(hh, dx, dy) (a.grad[(hh) & 7][0] * (dx) + a.grad[(hh) & 7][1] * (dy))
-            const double x1 = VX_GRAD(aa, xf, yf) * (1.0 - u) + VX_GRAD(ba, xf - 1.0, yf) * u;
-            const double x2 = VX_GRAD(ab, xf, yf - 1.0) * (1.0 - u) + VX_GRAD(bb, xf - 1.0, yf - 1.0) * u;
-#undef VX_GRAD
-            double nval = (x1 * (1.0 - v) + x2 * v) * 1.4142135623730951;
+            const double k0 = g[0][0], k1 = g[1][0] - g[0][0], k2 = g[0][1] - g[0][0], k3 = g[0][0] + g[1][1] - g[1][0] - g[0][1];
+            double nval = (k0 + k1 * u + k2 * v + k3 * u * v) * (2.0 / 1.4142135623730951);
             nval = nval < -1.0 ? -1.0 : (nval > 1.0 ? 1.0 : nval);
             const int hv = (int)trunc(nval * a.amplitude);
             h[lz][lx] = hv;

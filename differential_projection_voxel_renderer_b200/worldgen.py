@@ -8,11 +8,13 @@ Stone below, Air above, with the uniform shortcuts of chunk.rs:127-134
 -> Uniform(Stone)).
 
 The reference samples `noise 0.9.0` `Perlin::new(12345)`, a crates.io
-dependency that is not vendored under /root/reference, and no reference test
-pins a height value, so the exact heights are parity-unpinned.  They are input
-data: this module produces the voxel arrays once and the same bytes are fed to
-the CPU oracle and to the CUDA path.  The noise below is Ken Perlin's improved
-2-D gradient noise with a seed-shuffled permutation table.
+dependency that is not vendored under /root/reference.  Its published
+algorithm (XorShift-shuffled permutation table, perlin_2d with four diagonal
+gradients, quintic fade, bilinear blend, 2/sqrt(2) scale, clamp) is restated
+in the CPU restatement under oracle/; this module and the CUDA generator reproduce that
+restatement bit for bit (tests pin all three against each other).  No
+reference test pins a height value, so until tools/ref_dump vectors exist the
+heights are still parity-unpinned against the crate itself.
 """
 from __future__ import annotations
 
@@ -30,42 +32,61 @@ FACE_OFFSETS = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1]
 
 
 def _perm_table(seed: int) -> np.ndarray:
-    rng = np.random.RandomState(seed & 0x7FFFFFFF)
-    p = np.arange(256, dtype=np.int64)
-    rng.shuffle(p)
+    """`noise 0.9.0` PermutationTable::new(seed): XorShiftRng seeded with the bytes [1,0,0,0, seed, seed, seed] (LE),
+    then (0..256).shuffle(rng) as rand 0.8.5 does it (Fisher-Yates from the back, UniformInt<u32>::sample_single with the
+    widening-multiply / zone rejection).  Returned doubled (512 entries) for the device table."""
+    m32 = 0xFFFFFFFF
+    x, y, z, w = 1, seed & m32, seed & m32, seed & m32
+    if (x | y | z | w) == 0:
+        x = y = z = w = 0x0BAD5EED
+    vals = list(range(256))
+    for i in range(255, 0, -1):
+        rng_range = i + 1
+        lz = 32 - rng_range.bit_length()
+        zone = ((rng_range << lz) & m32) - 1
+        while True:
+            t = (x ^ (x << 11)) & m32
+            x, y, z = y, z, w
+            w = (w ^ (w >> 19) ^ (t ^ (t >> 8))) & m32
+            m = w * rng_range
+            if (m & m32) <= zone:
+                pick = m >> 32
+                break
+        vals[i], vals[pick] = vals[pick], vals[i]
+    p = np.asarray(vals, dtype=np.int64)
     return np.concatenate([p, p])
 
 
-_GRAD2 = np.array([[1, 1], [-1, 1], [1, -1], [-1, -1], [1, 0], [-1, 0], [0, 1], [0, -1]], dtype=np.float64)
-_GRAD2 /= np.maximum(np.linalg.norm(_GRAD2, axis=1, keepdims=True), 1.0)
+# gradients selected by hash & 3 (core/perlin.rs): +x+y, -x+y, +x-y, -x-y; the table is 8 long for the device struct
+_GRAD2 = np.array([[1, 1], [-1, 1], [1, -1], [-1, -1]] * 2, dtype=np.float64)
+_SCALE_2D = 2.0 / 1.4142135623730951  # 2 / core::f64::consts::SQRT_2
 
 
 def perlin2(x: np.ndarray, y: np.ndarray, seed: int = 12345) -> np.ndarray:
-    """Improved Perlin gradient noise, f64, output roughly in [-1, 1]."""
-    perm = _perm_table(seed)
-    xi = np.floor(x).astype(np.int64)
-    yi = np.floor(y).astype(np.int64)
-    xf = x - xi
-    yf = y - yi
-    xi &= 255
-    yi &= 255
+    """`noise 0.9.0` perlin_2d over PermutationTable::new(seed), f64, operation by operation as restated in
+    the CPU restatement under oracle/; output clamped to [-1, 1]."""
+    perm = _perm_table(seed)[:256]
+    cx = np.floor(x).astype(np.int64)
+    cy = np.floor(y).astype(np.int64)
+    dx = x - cx
+    dy = y - cy
 
-    def fade(t):
+    def quintic(t):
+        t = np.clip(t, 0.0, 1.0)
         return t * t * t * (t * (t * 6.0 - 15.0) + 10.0)
 
-    def grad(h, dx, dy):
-        g = _GRAD2[h & 7]
-        return g[..., 0] * dx + g[..., 1] * dy
+    def grad(ox, oy):
+        qx = dx - float(ox)
+        qy = dy - float(oy)
+        h = perm[perm[(cx + ox) & 255] ^ ((cy + oy) & 255)] & 3
+        return np.where(h == 0, qx + qy, np.where(h == 1, -qx + qy, np.where(h == 2, qx - qy, -qx - qy)))
 
-    aa = perm[perm[xi] + yi]
-    ab = perm[perm[xi] + yi + 1]
-    ba = perm[perm[xi + 1] + yi]
-    bb = perm[perm[xi + 1] + yi + 1]
-    u = fade(xf)
-    v = fade(yf)
-    x1 = grad(aa, xf, yf) * (1 - u) + grad(ba, xf - 1, yf) * u
-    x2 = grad(ab, xf, yf - 1) * (1 - u) + grad(bb, xf - 1, yf - 1) * u
-    return np.clip((x1 * (1 - v) + x2 * v) * 1.4142135623730951, -1.0, 1.0)
+    g00, g10, g01, g11 = grad(0, 0), grad(1, 0), grad(0, 1), grad(1, 1)
+    u = quintic(dx)
+    v = quintic(dy)
+    k0, k1, k2, k3 = g00, g10 - g00, g01 - g00, g00 + g11 - g10 - g01
+    unscaled = k0 + k1 * u + k2 * v + k3 * u * v
+    return np.clip(unscaled * _SCALE_2D, -1.0, 1.0)
 
 
 def terrain_heights(x0: int, z0: int, nx: int, nz: int, seed: int = 12345) -> np.ndarray:

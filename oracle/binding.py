@@ -135,6 +135,42 @@ def mesh_chunks(voxels, neighbors=None, uniform_flags=None, positions=None, cap_
     return MeshBatch(quads[:3 * tot].copy(), quad_base, quad_count, so, ab, hm, positions)
 
 
+def noise_permutation_table(seed: int = 12345) -> np.ndarray:
+    """noise 0.9.0 PermutationTable::new(seed).values (256,) u8."""
+    out = np.zeros(256, dtype=np.uint8)
+    lib().vxo_noise_permutation_table(C.c_uint32(seed), _p(out))
+    return out
+
+
+def perlin2(x: float, y: float, seed: int = 12345) -> float:
+    L = lib()
+    L.vxo_perlin2.restype = C.c_double
+    L.vxo_perlin2.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    return float(L.vxo_perlin2(_p(noise_permutation_table(seed)), float(x), float(y)))
+
+
+def terrain_heights(x0: int, z0: int, nx: int, nz: int, seed: int = 12345) -> np.ndarray:
+    """heights[z, x] = sample_terrain_height (chunk.rs:173-177) for world columns x0.., z0.."""
+    L = lib()
+    L.vxo_terrain_height.restype = C.c_int32
+    L.vxo_terrain_height.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    perm = noise_permutation_table(seed)
+    pp = _p(perm)
+    out = np.zeros((nz, nx), dtype=np.int32)
+    for z in range(nz):
+        for x in range(nx):
+            out[z, x] = L.vxo_terrain_height(pp, x0 + x, z0 + z)
+    return out
+
+
+def generate_terrain(position, seed: int = 12345):
+    """Chunk::generate_terrain (chunk.rs:114-170) -> (uniform flag 0 / 1 / 4, voxels (32768,) u8 -- zeros when Uniform)."""
+    pos = np.ascontiguousarray(position, dtype=np.int32).reshape(3)
+    vox = np.zeros(32768, dtype=np.uint8)
+    flag = int(lib().vxo_generate_terrain(_p(pos), C.c_uint32(seed), _p(vox)))
+    return flag, vox
+
+
 def frustum_from_vp(vp) -> np.ndarray:
     vp = np.ascontiguousarray(vp, dtype=np.float32).reshape(16)
     planes = np.zeros((6, 4), dtype=np.float32)

@@ -249,6 +249,102 @@ int64_t vxo_mesh_chunks(const uint8_t *voxels, const int32_t *neighbors, const u
 
 /* ---------- culling ---------------------------------------------------- */
 
+/* ----------------------------------------------------------------------------------------------
+ * Terrain generation: Chunk::generate_terrain (voxel/chunk.rs:114-207) over `noise 0.9.0` Perlin::new(12345).
+ *
+ * The `noise` crate (Cargo.lock: noise 0.9.0, rand 0.8.5, rand_xorshift 0.3.0) is a crates.io dependency that is NOT
+ * vendored under /root/reference and cannot be fetched here, so the functions below restate its published algorithm from
+ * the crate's source as documented:
+ *   PermutationTable::new(seed)  permutation_table.rs: 16 seed bytes = [1,0,0,0, seed_le, seed_le, seed_le] into
+ *                                XorShiftRng (rand_xorshift: t = x ^ x << 11; x,y,z = y,z,w; w = w ^ w >> 19 ^ t ^ t >> 8),
+ *                                then (0..256).shuffle(rng) with rand 0.8.5's SliceRandom::shuffle (i from len-1 down to
+ *                                1: swap(i, gen_range(0..i+1))) and UniformInt<u32>::sample_single (widening multiply,
+ *                                zone = (range << leading_zeros(range)) - 1, accept when the low word <= zone)
+ *   NoiseHasher::hash            values[values[x & 255] ^ (y & 255)]
+ *   perlin_2d                    core/perlin.rs: corner = floor(point), four gradients from hash & 3 over
+ *                                (+x+y, -x+y, +x-y, -x-y), quintic fade t^3 (t (6 t - 15) + 10) of the clamped distance,
+ *                                bilinear_interpolation k0 + k1 u + k2 v + k3 u v, scaled by 2 / sqrt(2), clamped to [-1, 1]
+ * No reference test pins a height, so until tools/ref_dump vectors exist these heights are PARITY UNPINNED (header of
+ * this file).  What IS pinned: the CUDA generator and the host generator reproduce this restatement bit for
+ * bit (tests/test_mesher_gpu.py, tests/test_oracle_kat.py).
+ * ---------------------------------------------------------------------------------------------- */
+void vxo_noise_permutation_table(uint32_t seed, uint8_t values[256]) {
+    uint32_t x = 1u, y = seed, z = seed, w = seed; /* le::read_u32_into of the 16 seed bytes */
+    if (x == 0 && y == 0 && z == 0 && w == 0) { x = 0x0BAD5EEDu; y = 0x0BAD5EEDu; z = 0x0BAD5EEDu; w = 0x0BAD5EEDu; }
+    for (int i = 0; i < 256; ++i) values[i] = (uint8_t)i;
+    for (uint32_t i = 255; i >= 1; --i) {
+        const uint32_t range = i + 1u; /* gen_range(0..i+1) */
+        const uint32_t zone = (range << __builtin_clz(range)) - 1u;
+        uint32_t pick;
+        for (;;) {
+            const uint32_t t = x ^ (x << 11);
+            x = y; y = z; z = w;
+            w = w ^ (w >> 19) ^ (t ^ (t >> 8));
+            const uint64_t m = (uint64_t)w * (uint64_t)range;
+            if ((uint32_t)m <= zone) { pick = (uint32_t)(m >> 32); break; }
+        }
+        const uint8_t tmp = values[i]; values[i] = values[pick]; values[pick] = tmp;
+    }
+}
+
+static inline double noise_quintic(double t) {
+    const double x = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+    return x * x * x * (x * (x * 6.0 - 15.0) + 10.0);
+}
+
+double vxo_perlin2(const uint8_t values[256], double px, double py) {
+    const double fx = floor(px), fy = floor(py);
+    const int64_t cx = (int64_t)fx, cy = (int64_t)fy;
+    const double dx = px - (double)cx, dy = py - (double)cy;
+    double g[2][2];
+    for (int ox = 0; ox < 2; ++ox)
+        for (int oy = 0; oy < 2; ++oy) {
+            const double qx = dx - (double)ox, qy = dy - (double)oy;
+            const unsigned h = values[values[(unsigned)((cx + ox) & 0xff)] ^ (unsigned)((cy + oy) & 0xff)] & 3u;
+            g[ox][oy] = h == 0 ? qx + qy : h == 1 ? -qx + qy : h == 2 ? qx - qy : -qx - qy;
+        }
+    const double u = noise_quintic(dx), v = noise_quintic(dy);
+    const double g00 = g[0][0], g10 = g[1][0], g01 = g[0][1], g11 = g[1][1];
+    const double k0 = g00, k1 = g10 - g00, k2 = g01 - g00, k3 = g00 + g11 - g10 - g01;
+    const double unscaled = k0 + k1 * u + k2 * v + k3 * u * v;
+    const double scaled = unscaled * (2.0 / 1.4142135623730951); /* 2 / core::f64::consts::SQRT_2 */
+    return scaled < -1.0 ? -1.0 : (scaled > 1.0 ? 1.0 : scaled);
+}
+
+/* sample_terrain_height chunk.rs:173-177 */
+int32_t vxo_terrain_height(const uint8_t values[256], int32_t x, int32_t z) {
+    const double n = vxo_perlin2(values, (double)x * 0.01, (double)z * 0.01);
+    return (int32_t)(n * 20.0); /* `as i32`: truncation, |n * 20| <= 20 */
+}
+
+/* Chunk::generate_terrain chunk.rs:114-170.  voxels_out: 32768 bytes (index z*1024 + y*32 + x, chunk.rs:52), written only
+ * for Varied chunks.  Returns the uniform flag: 0 Varied, 1 Uniform(Air), 4 Uniform(Stone) (1 + BlockType). */
+int vxo_generate_terrain(const int32_t pos[3], uint32_t seed, uint8_t *voxels_out) {
+    uint8_t values[256];
+    vxo_noise_permutation_table(seed, values);
+    int32_t h[CS][CS], mn = INT32_MAX, mx = INT32_MIN; /* [z][x]; get_height_range chunk.rs:191-207 */
+    for (int z = 0; z < CS; ++z)
+        for (int x = 0; x < CS; ++x) {
+            h[z][x] = vxo_terrain_height(values, pos[0] * CS + x, pos[2] * CS + z);
+            if (h[z][x] < mn) mn = h[z][x];
+            if (h[z][x] > mx) mx = h[z][x];
+        }
+    const int32_t y0 = pos[1] * CS;
+    if (y0 > mx) return 1;            /* all air above terrain :127-129 */
+    if (y0 + CS < mn - 10) return 4;  /* all solid below :132-134 */
+    for (int z = 0; z < CS; ++z)
+        for (int y = 0; y < CS; ++y)
+            for (int x = 0; x < CS; ++x) {
+                const int32_t wy = y0 + y, hh = h[z][x];
+                uint8_t t = 3;                 /* Stone */
+                if (wy > hh) t = 0;            /* Air   :145-146 */
+                else if (wy == hh) t = 1;      /* Grass */
+                else if (wy > hh - 3) t = 2;   /* Dirt  */
+                voxels_out[z * CS * CS + y * CS + x] = t;
+            }
+    return 0;
+}
+
 /* camera/mod.rs:123-160.  row(i) = (c0[i], c1[i], c2[i], c3[i]). */
 void vxo_frustum_from_vp(const float vp[16], float planes[24]) {
     float row[4][4];

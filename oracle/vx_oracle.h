@@ -71,6 +71,12 @@ int64_t vxo_mesh_chunks(const uint8_t *voxels, const int32_t *neighbors, const u
 /* ---- culling ---------------------------------------------------------- */
 
 /* camera/mod.rs:123-160.  vp is column-major (glam Mat4::to_cols_array). */
+/* terrain: noise 0.9.0 Perlin::new(seed) restated (see vx_oracle.c) + Chunk::generate_terrain chunk.rs:114-207 */
+void vxo_noise_permutation_table(uint32_t seed, uint8_t values[256]);
+double vxo_perlin2(const uint8_t values[256], double px, double py);
+int32_t vxo_terrain_height(const uint8_t values[256], int32_t x, int32_t z);
+int vxo_generate_terrain(const int32_t pos[3], uint32_t seed, uint8_t *voxels_out);
+
 void vxo_frustum_from_vp(const float vp[16], float planes[24]);
 /* camera/mod.rs:164-183 */
 int vxo_frustum_intersects_aabb(const float planes[24], const float mn[3], const float mx[3]);

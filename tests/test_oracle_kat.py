@@ -641,3 +641,52 @@ def test_occlusion_pass_only_drops_far_meshes_and_keeps_the_order(ob):
         if s1.size == s0.size:
             assert np.array_equal(c0, c1) and np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
     assert dropped_any
+
+
+# ---- terrain: noise 0.9.0 Perlin::new(12345) restated in the oracle, reproduced by the host generator -----------------------
+def test_noise_permutation_table_is_a_permutation_and_seed_dependent(ob):
+    t = ob.noise_permutation_table(12345)
+    assert sorted(t.tolist()) == list(range(256))
+    assert not np.array_equal(t, ob.noise_permutation_table(12346))
+    assert not np.array_equal(t, np.arange(256))
+    from differential_projection_voxel_renderer_b200 import worldgen
+    assert np.array_equal(worldgen._perm_table(12345)[:256], t) and np.array_equal(worldgen._perm_table(12345)[256:], t)
+    assert np.array_equal(worldgen._perm_table(7)[:256], ob.noise_permutation_table(7))
+
+
+def test_perlin_lattice_zeros_range_and_gradient_kat(ob):
+    """Properties that follow from perlin_2d itself (core/perlin.rs): the noise vanishes on the integer lattice (every
+    corner distance is 0 there), stays inside [-1, 1], and next to a lattice point it is the corner's gradient dotted with
+    the offset, scaled by 2/sqrt(2), up to the quintic fade's O(t^3) blend."""
+    for x, y in ((0.0, 0.0), (3.0, -7.0), (-12.0, 40.0), (255.0, 256.0)):
+        assert ob.perlin2(x, y) == 0.0
+    perm = ob.noise_permutation_table(12345).astype(np.int64)
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        cx, cy = (int(v) for v in rng.integers(-300, 300, size=2))
+        ex, ey = 1e-4 * rng.random(2)
+        h = int(perm[perm[cx & 255] ^ (cy & 255)]) & 3
+        g = (ex + ey, -ex + ey, ex - ey, -ex - ey)[h]
+        got = ob.perlin2(cx + ex, cy + ey)
+        assert abs(got - g * (2.0 / 1.4142135623730951)) < 1e-9
+    pts = rng.uniform(-50, 50, size=(2000, 2))
+    vals = np.array([ob.perlin2(a, b) for a, b in pts])
+    assert vals.min() >= -1.0 and vals.max() <= 1.0 and vals.std() > 0.1
+
+
+def test_host_terrain_generator_reproduces_the_oracle(ob):
+    from differential_projection_voxel_renderer_b200 import worldgen
+    for x0, z0 in ((0, 0), (-384, -384), (352, -96), (-1024, 992)):
+        assert np.array_equal(worldgen.terrain_heights(x0, z0, 32, 32), ob.terrain_heights(x0, z0, 32, 32))
+    pos = [(0, 0, 0), (0, -1, 0), (0, 1, 0), (3, 0, -5), (-12, 0, 11), (2, -2, 2), (7, -1, -7)]
+    w = worldgen.generate_world(np.asarray(pos, dtype=np.int32))
+    kinds = set()
+    for i, p in enumerate(pos):
+        flag, vox = ob.generate_terrain(p)
+        assert flag == int(w.uniform_flags[i]), p
+        kinds.add(flag)
+        if flag == 0:
+            assert np.array_equal(vox, w.voxels[i]), p
+    assert kinds == {0, 1, 4}
+    h = ob.terrain_heights(-64, -64, 128, 128)
+    assert -20 <= int(h.min()) < 0 < int(h.max()) <= 20  # (n * 20) as i32
