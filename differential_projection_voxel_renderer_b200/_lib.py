@@ -120,6 +120,7 @@ PROTOTYPES = {
     "vx_set_atlas": (C.c_int, [_P, C.POINTER(VxAtlas)]),
     "vx_render_frame": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig), _P, _P, _P, C.POINTER(_I)]),
     "vx_world_batch_create": (C.c_int, [_P, _I, C.POINTER(_P)]),
+    "vx_world_batch_grow": (C.c_int, [_P, _P, _I]),
     "vx_world_batch_assign": (C.c_int, [_P, _P, _P, _I, _P, _P]),
     "vx_world_batch_generate": (C.c_int, [_P, _P, _P, _I, _P, C.POINTER(VxTerrainParams), _P]),
     "vx_world_batch_unload": (C.c_int, [_P, _P, _P, _I]),

@@ -1100,6 +1100,45 @@ int vx_world_batch_create(VxContext *ctx, int32_t capacity, VxMeshBatch **out) {
     return VX_OK;
 }
 
+// The reference's world is a HashMap that simply grows (world.rs:30-100: a moving camera that keeps hitting
+// max_chunks_per_frame never reaches the unload step; World::set_view_distance widens the sphere at run time).  A world
+// batch grows the same way: more slots, everything already loaded -- voxels, flags, neighbour rows, meshes, the quad
+// stream -- is kept (device-to-device copies), the new slots are absent chunks.
+int vx_world_batch_grow(VxContext *ctx, VxMeshBatch *b, int32_t new_capacity) {
+    if (!ctx || !b || !b->owns_world || !b->has_neighbors) return vx_fail(ctx, VX_ERR_INVALID, "vx_world_batch_grow: not a world batch");
+    if (new_capacity <= b->n_chunks) return VX_OK;
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t n0 = (size_t)b->n_chunks, n1 = (size_t)new_capacity;
+    auto grow = [&](VxDeviceBuffer &buf, size_t per, int fill) -> cudaError_t {
+        VxDeviceBuffer fresh;
+        cudaError_t e = fresh.reserve(n1 * per + 16);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(fresh.ptr, buf.ptr, n0 * per, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(static_cast<uint8_t *>(fresh.ptr) + n0 * per, fill, (n1 - n0) * per, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            fresh.release();
+            return e;
+        }
+        buf.release();
+        buf = fresh;
+        return cudaSuccess;
+    };
+    VX_CUDA(ctx, grow(b->world_voxels, VX_CHUNK_VOLUME, 0));
+    VX_CUDA(ctx, grow(b->world_neighbors, 6 * sizeof(int32_t), 0xFF)); // VX_NBR_NONE
+    VX_CUDA(ctx, grow(b->world_flags, 1, 1));                          // "uniform air": an absent chunk
+    VX_CUDA(ctx, grow(b->positions, 3 * sizeof(int32_t), 0));
+    VX_CUDA(ctx, grow(b->has_mesh, 1, 0));
+    VX_CUDA(ctx, grow(b->quad_count, sizeof(uint32_t), 0));
+    VX_CUDA(ctx, grow(b->quad_base, sizeof(uint32_t), 0));
+    VX_CUDA(ctx, grow(b->slice_offsets, 198 * sizeof(uint32_t), 0));
+    VX_CUDA(ctx, grow(b->face_aabb, 36 * sizeof(int32_t), 0));
+    b->host_neighbors.resize(n1 * 6, -1);
+    b->n_chunks = new_capacity;
+    return VX_OK;
+}
+
 static int world_check_slots(VxContext *ctx, const VxMeshBatch *b, const int32_t *slots, int32_t n, const char *who) {
     if (!ctx || !b || n < 0 || (n > 0 && !slots)) return vx_fail(ctx, VX_ERR_INVALID, who);
     if (!b->owns_world || !b->has_neighbors) return vx_fail(ctx, VX_ERR_INVALID, "not a world batch (vx_world_batch_create)");

@@ -3,6 +3,8 @@
 // vertex dump used by the parity tests.                      (compiled with -fmad=false, see vx_math.cuh)
 #include "vx_common.cuh"
 
+#include <cmath>
+
 #include <math_constants.h>
 #include "vx_math.cuh"
 
@@ -148,8 +150,11 @@ VxMat4 to_mat(const float vp[16]) {
 // ------------------------------------------------------------------------------------------------
 // culling::apply_horizon_culling (culling.rs:40-119).  One CTA.  The reference is a serial front-to-back sweep with a
 // running horizon per angular bin; bins are independent, so after the stable distance sort every bin is swept by its
-// own thread.  atan2 is evaluated in f64 and rounded to f32 (the reference calls the platform libm's atan2f; results
-// can differ from it only for meshes whose angle falls within an ulp of a bin boundary -- DESIGN.md 8).
+// own thread.  The angle of every candidate is an input: the reference calls the platform libm's atan2f
+// (culling.rs:86, Rust std on Linux = the C library's atan2f), whose last bit no device routine is specified to
+// reproduce, and one ulp decides the bin of a mesh that sits on a bin boundary (lattice-aligned chunk centres do, e.g.
+// on the diagonals).  vx_horizon_cull therefore evaluates atan2f for its n candidates on the host -- the same call
+// the reference makes -- and hands the kernel the angles; everything else runs here.
 // ------------------------------------------------------------------------------------------------
 constexpr int HZ_THREADS = 1024;
 
@@ -159,6 +164,8 @@ struct HorizonArgs {
     int32_t n, bins;
     float cam[3];
     float base_margin, margin_dist_factor, min_dist_chunks;
+    const float *angle_in; // [n] atan2f(center.z - cam.z, center.x - cam.x) of order[i] (host libm, see above)
+    float *angle;         // [n] scratch: the same in sorted order
     float *key;           // [n] scratch: distance_sq in input order
     int32_t *sorted;      // [n] scratch: ids sorted by distance
     int32_t *bin_of;      // [n] scratch: bin of sorted[i], -1 = always kept
@@ -187,6 +194,7 @@ __global__ void __launch_bounds__(HZ_THREADS) horizon_cull_kernel(HorizonArgs a)
             rank += (kj < k || (kj == k && j < i)) ? 1 : 0;
         }
         a.sorted[rank] = a.order[i];
+        a.angle[rank] = a.angle_in[i];
     }
     __syncthreads();
     // per-mesh quantities
@@ -201,7 +209,7 @@ __global__ void __launch_bounds__(HZ_THREADS) horizon_cull_kernel(HorizonArgs a)
         if (!(dist_xz < 1e-3f)) {
             const float dist_chunks = dist_xz / chunk_size;
             if (!(dist_chunks < a.min_dist_chunks)) {
-                const float angle = (float)atan2((double)tz, (double)tx);
+                const float angle = a.angle[i];
                 const float bin_f = (angle + PI) / (2.0f * PI) * (float)a.bins;
                 long b = (long)vx_f2i(floorf(bin_f));
                 if (b < 0) b += a.bins;
@@ -468,12 +476,23 @@ int vx_horizon_cull(VxContext *ctx, const float cam_pos[3], const float *centers
     const size_t off_order = sizeof(float) * 3 * (size_t)n_centers;
     const size_t off_key = off_order + 4 * nn, off_sorted = off_key + 4 * nn, off_bin = off_sorted + 4 * nn;
     const size_t off_slope = off_bin + 4 * nn, off_margin = off_slope + 4 * nn, off_top = off_margin + 4 * nn;
-    const size_t off_keep = off_top + 4 * nn, off_cnt = (off_keep + nn + 15) & ~(size_t)15;
+    const size_t off_ang_in = off_top + 4 * nn, off_ang = off_ang_in + 4 * nn;
+    const size_t off_keep = off_ang + 4 * nn, off_cnt = (off_keep + nn + 15) & ~(size_t)15;
     VX_CUDA(ctx, ctx->tmp_a.reserve(off_cnt + 16));
     uint8_t *base = ctx->tmp_a.as<uint8_t>();
+    // xz.y.atan2(xz.x) (culling.rs:86) with the platform's atan2f, exactly as the reference evaluates it
+    std::vector<float> ang(nn);
+    for (size_t i = 0; i < nn; ++i) {
+        const float *c = centers + 3 * (size_t)order_inout[i];
+        const float tx = c[0] - cam_pos[0], tz = c[2] - cam_pos[2];
+        ang[i] = atan2f(tz, tx);
+    }
     VX_CUDA(ctx, cudaMemcpyAsync(base, centers, off_order, cudaMemcpyHostToDevice, ctx->stream));
     VX_CUDA(ctx, cudaMemcpyAsync(base + off_order, order_inout, 4 * nn, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx, cudaMemcpyAsync(base + off_ang_in, ang.data(), 4 * nn, cudaMemcpyHostToDevice, ctx->stream));
     HorizonArgs a;
+    a.angle_in = reinterpret_cast<const float *>(base + off_ang_in);
+    a.angle = reinterpret_cast<float *>(base + off_ang);
     a.centers = reinterpret_cast<const float *>(base);
     a.order = reinterpret_cast<int32_t *>(base + off_order);
     a.n = n;

@@ -67,6 +67,11 @@ class _DeviceWorld:
         self.ctx.check(self.ctx.lib.vx_world_batch_assign(self.ctx.handle, self.batch.handle, api._p(slots), int(slots.size), None,
                                                           api._p(neighbors)))
 
+    def grow(self, capacity: int):
+        self.ctx.check(self.ctx.lib.vx_world_batch_grow(self.ctx.handle, self.batch.handle, int(capacity)))
+        self.batch._n_chunks = int(capacity)
+        self.batch._host = None
+
     def unload(self, slots: np.ndarray):
         self.ctx.check(self.ctx.lib.vx_world_batch_unload(self.ctx.handle, self.batch.handle, api._p(slots), int(slots.size)))
 
@@ -164,7 +169,9 @@ class World:
         if not new:
             return
         if len(new) > len(self._free):
-            raise RuntimeError(f"world batch full: {len(self.chunks)} chunks loaded, capacity {self.capacity}")
+            # The reference's HashMap just grows: a camera that keeps moving hits max_chunks_per_frame every frame, returns
+            # before the unload step (world.rs:84-87) and so never unloads.  Grow the device batch the same way.
+            self._grow(max(2 * self.capacity, self.capacity + len(new)))
         slots = np.array([self._free.pop() for _ in new], dtype=np.int32)
         for p, s in zip(new, slots.tolist()):
             self.chunks[p] = s
@@ -175,6 +182,23 @@ class World:
         for p in new:  # the chunks next to a new one now have a neighbour there
             touched += [(p[0] + o[0], p[1] + o[1], p[2] + o[2]) for o in FACE_OFFSETS]
         self._push_neighbor_rows(touched)
+
+    def _grow(self, capacity: int):
+        if capacity <= self.capacity:
+            return
+        self.device.grow(capacity)
+        self._free = list(range(capacity - 1, self.capacity - 1, -1)) + self._free
+        self.capacity = capacity
+
+    def set_view_distance(self, view_distance: int):  # world.rs:181-184 (main.rs:168-176 calls it at run time)
+        self.config.view_distance = max(1, int(view_distance))
+
+    def view_distance(self) -> int:  # world.rs:187-189
+        return self.config.view_distance
+
+    def clear(self):  # world.rs:192-195
+        self._unload(sorted(self.chunks))
+        self.last_camera_chunk = None
 
     def _unload(self, gone: List[Pos]):
         if not gone:

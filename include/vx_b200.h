@@ -204,6 +204,11 @@ VX_API int vx_generate_terrain(VxContext *ctx, const int32_t *positions, int32_t
  * "uniform air without neighbours": it has no mesh and is an absent neighbour (faces towards it are exposed,
  * binary_greedy.rs:127-168 with a missing map entry). ---- */
 VX_API int vx_world_batch_create(VxContext *ctx, int32_t capacity, VxMeshBatch **out);
+/* More slots for a world batch; everything loaded stays (voxels, flags, neighbour rows, meshes, quad stream).  The
+ * reference's chunk map grows without bound while the camera moves (world.rs:84-87 returns before the unload step on
+ * every frame that hits max_chunks_per_frame) and World::set_view_distance widens the sphere at run time
+ * (world.rs:181-198, called from main.rs:168-176). */
+VX_API int vx_world_batch_grow(VxContext *ctx, VxMeshBatch *b, int32_t new_capacity);
 /* positions (n x 3, may be NULL) and neighbour rows (n x 6: slot of the chunk in direction +X,-X,+Y,-Y,+Z,-Z or
  * VX_NBR_NONE; may be NULL) of the listed slots. */
 VX_API int vx_world_batch_assign(VxContext *ctx, VxMeshBatch *b, const int32_t *slots, int32_t n, const int32_t *positions,

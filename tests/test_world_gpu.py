@@ -103,3 +103,49 @@ def test_world_batch_compaction_keeps_meshes(ctx, ob):
     with pytest.raises(api.VxError):
         w.device.remesh(np.array([w.capacity], dtype=np.int32))
     w.batch.release()
+
+
+def test_world_batch_grows_and_keeps_everything(ctx, ob):
+    """vx_world_batch_grow (the reference's chunk map grows without bound under a moving camera, world.rs:84-87): a world
+    started in a batch that is far too small ends up identical -- loaded set, meshes, rendered frame -- to one that had
+    room from the start, and a moving camera follows the reference loop frame by frame across several growth steps."""
+    vd = 2
+    big = vxw.World(vxw.WorldConfig(view_distance=vd, max_chunks_per_frame=1000), ctx=ctx)
+    small = vxw.World(vxw.WorldConfig(view_distance=vd, max_chunks_per_frame=1000), ctx=ctx, capacity=5)
+    W, H = 320, 180
+    cfg = api.default_frame_config(W, H)
+    cb, cs = vxw.MeshCache(big), vxw.MeshCache(small)
+    for step, pos in enumerate([(0.0, 10.0, 20.0), (40.0, 14.0, -20.0), (75.0, 20.0, -40.0)]):
+        cam = camera.Camera(pos, W / H, yaw=0.4 * step, pitch=-0.2)
+        vp = cam.view_projection()
+        c0, d0, s0 = vxw.frame(big, cb, cam.position, vp, cfg, ctx)
+        c1, d1, s1 = vxw.frame(small, cs, cam.position, vp, cfg, ctx)
+        assert sorted(big.chunks) == sorted(small.chunks) and small.capacity >= small.chunk_count()
+        assert np.array_equal(c0, c1) and np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
+        inv0 = {s: p for p, s in big.chunks.items()}
+        inv1 = {s: p for p, s in small.chunks.items()}
+        assert [inv0[s] for s in s0.tolist()] == [inv1[s] for s in s1.tolist()]
+    assert small.capacity > 5
+    big.batch.release()
+    small.batch.release()
+    # moving camera, never unloading: chunk for chunk like the reference loop
+    ref = vx_refloop.RefLoop(ob, vd, 4)
+    w = vxw.World(vxw.WorldConfig(view_distance=vd, max_chunks_per_frame=4), ctx=ctx)
+    cap0 = w.capacity
+    for step in range(110):
+        pos = (16.0 * step, 10.0, 20.0)
+        assert ref.update(pos) == w.update(pos)
+        assert sorted(w.chunks) == sorted(ref.chunks)
+    assert w.capacity > cap0 and w.chunk_count() > cap0
+    cache = vxw.MeshCache(w)  # every chunk loaded before or after the growth meshes like the reference's
+    vis = sorted(w.chunks)
+    ref.update_cache(vis)
+    cache.update(vis)
+    got = w.batch.download()
+    for p, m in ref.mesh_cache.items():
+        s = w.chunks[p]
+        assert (m is None) == (got["has_mesh"][s] == 0)
+        if m is not None:
+            b, c = int(got["quad_base"][s]), int(got["quad_count"][s])
+            assert np.array_equal(got["quads"][b:b + c], m[0].reshape(-1, 3))
+    w.batch.release()

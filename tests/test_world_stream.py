@@ -39,6 +39,13 @@ class FakeDevice:
             self.nbr[s] = list(row)
         self.calls.append(("assign", slots.tolist()))
 
+    def grow(self, capacity):
+        assert capacity > self.capacity
+        for s in range(self.capacity, capacity):
+            self.nbr[s] = [-1] * 6
+        self.capacity = capacity
+        self.calls.append(("grow", capacity))
+
     def unload(self, slots):
         for s in slots.tolist():
             del self.pos[s], self.flag[s], self.vox[s]
@@ -121,6 +128,43 @@ def test_world_update_cap_returns_before_unloading(ob):
     assert w.chunk_count() == 7 and len(w.unloaded_last_update) == 7
     assert not w.update((32.0 * 10, 0.0, 0.0))      # nothing left to do
     assert vxw.world_to_chunk_pos((-0.5, 31.9, 32.0)) == (-1, 0, 1)  # world.rs:201-207
-    with pytest.raises(RuntimeError):
-        small = vxw.World(vxw.WorldConfig(view_distance=1, max_chunks_per_frame=1000), device=FakeDevice(ob, 3), capacity=3)
-        small.update((0.0, 0.0, 0.0))
+    # a batch that is too small grows (the reference's HashMap has no capacity): nothing is lost, slots stay unique
+    dev3 = FakeDevice(ob, 3)
+    small = vxw.World(vxw.WorldConfig(view_distance=1, max_chunks_per_frame=1000), device=dev3, capacity=3)
+    small.update((0.0, 0.0, 0.0))
+    assert small.chunk_count() == 7 and small.capacity >= 7 and any(c[0] == "grow" for c in dev3.calls)
+    assert sorted(small.chunks.values()) == sorted(set(small.chunks.values())) and max(small.chunks.values()) < small.capacity
+
+
+def test_moving_camera_never_unloads_and_the_world_grows_like_the_reference(ob):
+    """A camera that keeps moving hits max_chunks_per_frame on every update, so the reference returns before its unload
+    step (world.rs:84-87) and its chunk map just grows -- far beyond the view sphere.  The port follows it chunk for chunk
+    (same loaded set every frame) by growing the device batch; set_view_distance (world.rs:181-184, main.rs:168-176)
+    takes effect at the next update."""
+    vd, cap = 2, 4
+    ref = vx_refloop.RefLoop(ob, vd, cap)
+    dev = FakeDevice(ob, vxw.sphere_capacity(vd))
+    w = vxw.World(vxw.WorldConfig(view_distance=vd, max_chunks_per_frame=cap), device=dev)
+    first_capacity = w.capacity
+    for step in range(160):
+        pos = (16.0 * step, 10.0, 20.0)  # half a chunk per frame
+        assert ref.update(pos) == w.update(pos)
+        assert sorted(w.chunks) == sorted(ref.chunks), f"step {step}"
+        assert w.unloaded_last_update == []
+    assert w.chunk_count() > first_capacity and w.capacity > first_capacity and any(c[0] == "grow" for c in dev.calls)
+    assert len(set(w.chunks.values())) == len(w.chunks) and max(w.chunks.values()) < w.capacity
+    for p, s in w.chunks.items():  # neighbour rows survived the growth
+        assert dev.nbr[s] == [w.chunks.get((p[0] + o[0], p[1] + o[1], p[2] + o[2]), -1) for o in vxw.FACE_OFFSETS]
+    # standing still lets the unload step run; widening the view distance loads the bigger sphere
+    for _ in range(40):
+        ref.update(pos)
+        w.update(pos)
+    assert sorted(w.chunks) == sorted(ref.chunks) and w.chunk_count() <= vxw.sphere_capacity(vd)
+    w.set_view_distance(3)
+    ref.vd = 3
+    for _ in range(60):
+        ref.update(pos)
+        w.update(pos)
+    assert w.view_distance() == 3 and sorted(w.chunks) == sorted(ref.chunks) and w.chunk_count() > vxw.sphere_capacity(2) // 2
+    w.set_view_distance(0)
+    assert w.view_distance() == 1  # .max(1)
