@@ -304,10 +304,9 @@ def run_cuda(args):
         if comp is None:
             api.render_frame_device(batch, vp, cam.position, cfg_async, VD, ctx)
         else:
-            comp.render(batch, vp, cam.position, cfg, VD, frame_no)
+            comp.render(batch, vp, cam.position, cfg, VD, frame_no)  # hand-off fused into the raster kernel
             if rank == 0:
-                comp.complete(frame_no)  # every stripe of this frame has landed in GPU0's memory
-                comp.release(frame_no)
+                comp.complete_and_release(frame_no)  # one kernel: every stripe of this frame has landed in GPU0's memory -> buffer free
         frame_no += 1
 
     # ---- warm-up ---------------------------------------------------------------------------------------------------
@@ -462,15 +461,16 @@ def run_cuda(args):
             e2e_no[0] += 1
             comp.render(batch, vp, cam.position, cfg, VD, k)
             if rank == 0:
-                comp.complete(k)
+                if k >= 1:  # frame k - 1 has left GPU0 (stream order): its buffer is handed back with this frame's arrival wait
+                    stream.wait_event(copied[(j - 1) & 1])
+                    comp.complete_and_release(k, k - 1)
+                else:
+                    comp.complete(k)
                 composed[j & 1].record(stream)
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(composed[j & 1])
                     host_t[j & 1].copy_(comp.frame_tensor(k, dev), non_blocking=True)
                     copied[j & 1].record(copy_stream)
-                if k >= 1:  # frame k - 1 has left GPU0 (or will have, in stream order): its buffer may be re-used
-                    stream.wait_event(copied[(j - 1) & 1])
-                    comp.release(k - 1)
             submitted[j & 1].record(stream)
 
         def e2e_wait(j):
@@ -851,8 +851,7 @@ def bench_cfg5(torch, api, multigpu, sharding, ctx, stream, dev, rank, world_siz
         def step():
             comp5.render(batch5, vp5, cam5.position, c5, VD5, kk[0])
             if rank == 0:
-                comp5.complete(kk[0])
-                comp5.release(kk[0])
+                comp5.complete_and_release(kk[0])
             kk[0] += 1
 
         ms_comp = timed(step)

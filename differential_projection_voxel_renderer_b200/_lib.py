@@ -65,6 +65,11 @@ class VxMeshBatchDevice(C.Structure):
                 ("d_positions", C.c_void_p)]
 
 
+class VxStripeSync(C.Structure):
+    _fields_ = [("d_wait_flag", C.c_void_p), ("wait_value", C.c_uint32), ("d_signal_flag", C.c_void_p), ("signal_value", C.c_uint32),
+                ("timeout_us", C.c_int32)]
+
+
 class VxShardLayout(C.Structure):
     _fields_ = [("rank_stride", C.c_int64), ("off_quad_base", C.c_int64), ("off_quad_count", C.c_int64),
                 ("off_slice_offsets", C.c_int64), ("off_face_aabb", C.c_int64), ("off_has_mesh", C.c_int64),
@@ -97,6 +102,7 @@ PROTOTYPES = {
     "vx_ipc_close": (C.c_int, [_P, _P]),
     "vx_signal_flags": (C.c_int, [_P, _P, _I, C.c_uint32]),
     "vx_wait_flags": (C.c_int, [_P, _P, _I, _I, C.c_uint32, _I]),
+    "vx_wait_then_signal": (C.c_int, [_P, _P, _I, _I, C.c_uint32, _P, _I, C.c_uint32, _I]),
     "vx_wait_status": (C.c_int, [_P, C.POINTER(_I)]),
     "vx_shard_layout": (C.c_int, [_I, C.c_int64, C.POINTER(VxShardLayout)]),
     "vx_mesh_shard_pack": (C.c_int, [_P, _P, C.POINTER(VxShardLayout), _P]),
@@ -134,6 +140,7 @@ PROTOTYPES = {
     "vx_hyper_pipeline_render": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _P, _P, C.POINTER(_I)]),
     "vx_render_frame_begin": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig), _P, _P, C.POINTER(_I)]),
     "vx_render_frame_end": (C.c_int, [_P, _I, _P, C.POINTER(_I)]),
+    "vx_render_frame_stripe": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig), _P, _P, C.POINTER(VxStripeSync)]),
     "vx_render_frame_device": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig)]),
     "vx_render_frame_into": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig), _P, _P]),
     "vx_framebuffer_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I), C.POINTER(_I)]),

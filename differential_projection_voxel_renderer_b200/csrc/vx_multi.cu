@@ -58,6 +58,36 @@ __global__ void wait_flags_kernel(const uint32_t *flags, int n, int stride_words
     }
 }
 
+// wait for n_wait local flag words, then publish `sv` into n_signal flag words (one warp)
+__global__ void wait_then_signal_kernel(const uint32_t *flags, int n, int stride_words, uint32_t value, unsigned long long timeout_ns, uint32_t *status,
+                                        uint32_t *const *sig, int n_sig, uint32_t sv) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const int lane = threadIdx.x;
+    bool timed_out = false;
+    for (int base = 0; base < n && !timed_out; base += 32) {
+        const int i = base + lane;
+        while (true) {
+            uint32_t v = value;
+            if (i < n) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + (size_t)i * stride_words) : "memory");
+            if (__all_sync(0xffffffffu, (int32_t)(v - value) >= 0)) break;
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > timeout_ns) {
+                timed_out = true;
+                break;
+            }
+            __nanosleep(40);
+        }
+    }
+    __threadfence_system();
+    if (timed_out) {
+        if (lane == 0 && status) status[0] = 1u;
+        return; // nothing is acknowledged for a frame that never arrived
+    }
+    if (lane < n_sig && sig[lane]) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(sig[lane]), "r"(sv) : "memory");
+}
+
 } // namespace
 
 extern "C" {
@@ -138,6 +168,29 @@ int vx_wait_flags(VxContext *ctx, const uint32_t *d_flags, int32_t n, int32_t st
     }
     const unsigned long long ns = (unsigned long long)(timeout_us > 0 ? timeout_us : 2000000) * 1000ull;
     wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(d_flags, n, stride_words, value, ns, ctx->multi_status.as<uint32_t>());
+    VX_CHECK_LAUNCH(ctx);
+    return VX_OK;
+}
+
+int vx_wait_then_signal(VxContext *ctx, const uint32_t *d_wait_flags, int32_t n_wait, int32_t stride_words, uint32_t wait_value,
+                        uint32_t *const *d_signal_flags, int32_t n_signal, uint32_t signal_value, int32_t timeout_us) {
+    if (!ctx || n_wait < 0 || (n_wait > 0 && !d_wait_flags) || stride_words < 1 || n_signal < 0 || n_signal > 32 || (n_signal > 0 && !d_signal_flags))
+        return vx_fail(ctx, VX_ERR_INVALID, "vx_wait_then_signal: bad argument (at most 32 flags to signal)");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->multi_status.ptr) {
+        VX_CUDA(ctx, ctx->multi_status.reserve(16));
+        VX_CUDA(ctx, cudaMemsetAsync(ctx->multi_status.ptr, 0, 16, ctx->stream));
+    }
+    VX_CUDA(ctx, ctx->multi_ptrs.reserve(sizeof(uint32_t *) * 32));
+    if (n_signal > 0 && (ctx->multi_ptrs_n != n_signal || memcmp(ctx->multi_ptrs_host, d_signal_flags, sizeof(uint32_t *) * (size_t)n_signal) != 0)) {
+        VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // an earlier kernel may still read the table
+        memcpy(ctx->multi_ptrs_host, d_signal_flags, sizeof(uint32_t *) * (size_t)n_signal);
+        ctx->multi_ptrs_n = n_signal;
+        VX_CUDA(ctx, cudaMemcpyAsync(ctx->multi_ptrs.ptr, ctx->multi_ptrs_host, sizeof(uint32_t *) * (size_t)n_signal, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const unsigned long long ns = (unsigned long long)(timeout_us > 0 ? timeout_us : 2000000) * 1000ull;
+    wait_then_signal_kernel<<<1, 32, 0, ctx->stream>>>(d_wait_flags, n_wait, stride_words, wait_value, ns, ctx->multi_status.as<uint32_t>(),
+                                                       ctx->multi_ptrs.as<uint32_t *>(), n_signal, signal_value);
     VX_CHECK_LAUNCH(ctx);
     return VX_OK;
 }

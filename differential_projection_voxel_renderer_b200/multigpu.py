@@ -20,7 +20,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import api
-from ._lib import VxShardLayout
+from ._lib import VxShardLayout, VxStripeSync
 
 FLAG_STRIDE_WORDS = 32  # one 128-byte line per flag
 
@@ -123,17 +123,27 @@ class StripeCompositor:
     def render(self, batch: api.MeshBatch, view_proj, camera_position, cfg, view_distance: int, frame_no: int):
         """Enqueue this rank's stripe of frame `frame_no` (asynchronous; cfg is copied with the stripe filled in)."""
         ctx, lib, h = self.ctx, self.ctx.lib, self.ctx.handle
-        if frame_no >= self.n_buffers:  # the buffer is free once dst has consumed frame_no - n_buffers
-            ctx.check(lib.vx_wait_flags(h, self.ack_local, 1, 1, frame_no - self.n_buffers + 1, self.timeout_us))
         y0, rows = self.stripes[self.rank]
+        arrive = self.arrive + 4 * FLAG_STRIDE_WORDS * self.rank
+        wait_needed = frame_no >= self.n_buffers  # the buffer is free once dst has consumed frame_no - n_buffers
         if rows > 0:
+            # hand-off fused into the raster kernel: it waits for the acknowledgement before its first store into the frame
+            # and its last CTA publishes the arrival word -- three launches per stripe, none of them a hand-off kernel
             c = api.VxFrameConfig.from_buffer_copy(cfg)
-            c.stripe_y0, c.stripe_rows, c.async_submit = y0, rows, 1
+            c.stripe_y0, c.stripe_rows = y0, rows
             off = y0 * self.W * 4
-            api.render_frame_into(batch, view_proj, camera_position, c, view_distance, self.color_ptr(frame_no) + off,
-                                  (self.depth_ptr(frame_no) + off) if self.want_depth else 0, ctx)
-        flag = (C.c_void_p * 1)(self.arrive + 4 * FLAG_STRIDE_WORDS * self.rank)
-        ctx.check(lib.vx_signal_flags(h, flag, 1, frame_no + 1))
+            sync = VxStripeSync(self.ack_local.value if wait_needed else None, (frame_no - self.n_buffers + 1) & 0xFFFFFFFF if wait_needed else 0,
+                                arrive, (frame_no + 1) & 0xFFFFFFFF, self.timeout_us)
+            vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+            cam = np.ascontiguousarray(camera_position, dtype=np.float32).reshape(3)
+            ctx.check(lib.vx_render_frame_stripe(h, batch.handle, None, -1, api._p(vp), api._p(cam), int(view_distance), C.byref(c),
+                                                 C.c_void_p(self.color_ptr(frame_no) + off),
+                                                 C.c_void_p(self.depth_ptr(frame_no) + off) if self.want_depth else None, C.byref(sync)))
+        else:  # a rank without rows only reports in
+            if wait_needed:
+                ctx.check(lib.vx_wait_flags(h, self.ack_local, 1, 1, frame_no - self.n_buffers + 1, self.timeout_us))
+            flag = (C.c_void_p * 1)(arrive)
+            ctx.check(lib.vx_signal_flags(h, flag, 1, frame_no + 1))
 
     def complete(self, frame_no: int):
         """dst only: enqueue the wait for every rank's stripe of `frame_no`; later work on the stream sees the frame."""
@@ -145,6 +155,15 @@ class StripeCompositor:
         assert self.rank == self.dst
         flags = (C.c_void_p * self.world)(*self.acks)
         self.ctx.check(self.ctx.lib.vx_signal_flags(self.ctx.handle, flags, self.world, frame_no + 1))
+
+    def complete_and_release(self, frame_no: int, release_frame_no: Optional[int] = None):
+        """dst only: one kernel that waits for every stripe of `frame_no` and then hands the buffer of `release_frame_no`
+        (default: the same frame) back to all ranks."""
+        assert self.rank == self.dst
+        rel = frame_no if release_frame_no is None else release_frame_no
+        flags = (C.c_void_p * self.world)(*self.acks)
+        self.ctx.check(self.ctx.lib.vx_wait_then_signal(self.ctx.handle, C.c_void_p(self.arrive), self.world, FLAG_STRIDE_WORDS, (frame_no + 1) & 0xFFFFFFFF,
+                                                        flags, self.world, (rel + 1) & 0xFFFFFFFF, self.timeout_us))
 
     def check(self):
         """Synchronise and raise if a wait timed out."""

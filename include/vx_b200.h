@@ -177,6 +177,10 @@ VX_API int vx_ipc_open(VxContext *ctx, const uint8_t handle[64], void **d_out);
 VX_API int vx_ipc_close(VxContext *ctx, void *d_ptr);
 VX_API int vx_signal_flags(VxContext *ctx, uint32_t *const *d_flags, int32_t n, uint32_t value);
 VX_API int vx_wait_flags(VxContext *ctx, const uint32_t *d_flags, int32_t n, int32_t stride_words, uint32_t value, int32_t timeout_us);
+/* vx_wait_flags followed by vx_signal_flags in ONE kernel (the composing GPU's per-frame step: every stripe has
+ * arrived -> hand the buffer of an older frame back to all ranks). */
+VX_API int vx_wait_then_signal(VxContext *ctx, const uint32_t *d_wait_flags, int32_t n_wait, int32_t stride_words, uint32_t wait_value,
+                        uint32_t *const *d_signal_flags, int32_t n_signal, uint32_t signal_value, int32_t timeout_us);
 VX_API int vx_wait_status(VxContext *ctx, int32_t *timed_out);
 
 /* ---- terrain generation (the step before meshing) -------------------- */
@@ -360,6 +364,24 @@ VX_API int vx_render_frame_device(VxContext *ctx, const VxMeshBatch *batch, cons
 VX_API int vx_render_frame_into(VxContext *ctx, const VxMeshBatch *batch, const int32_t *d_mesh_ids, int32_t n_meshes,
                          const float vp[16], const float cam_pos[3], int32_t view_distance, const VxFrameConfig *cfg,
                          uint32_t *d_color_dst, float *d_depth_dst);
+/* Stripe of a frame that is composed on another GPU (one process per GPU; framebuffer.rs:392-431 hands disjoint
+ * `&mut` stripes of ONE framebuffer to the workers): as vx_render_frame_into with d_color_dst / d_depth_dst pointing
+ * into the peer-mapped frame (vx_ipc_open), plus the hand-off fused into the raster kernel -- before its first store
+ * the kernel waits until *d_wait_flag (a word in THIS GPU's memory, written by the composing GPU when it has consumed
+ * the frame that last used the buffer) has reached wait_value; after its last store the last CTA publishes signal_value
+ * into *d_signal_flag (the composing GPU's arrival word for this rank) with release semantics at system scope.  Either
+ * pointer may be NULL.  Always asynchronous (like cfg->async_submit = 1); a wait that exceeds timeout_us (<= 0: 2 s) is
+ * reported by vx_frame_stats, nothing hangs. */
+typedef struct {
+    const uint32_t *d_wait_flag;
+    uint32_t wait_value;
+    uint32_t *d_signal_flag;
+    uint32_t signal_value;
+    int32_t timeout_us;
+} VxStripeSync;
+VX_API int vx_render_frame_stripe(VxContext *ctx, const VxMeshBatch *batch, const int32_t *d_mesh_ids, int32_t n_meshes,
+                           const float vp[16], const float cam_pos[3], int32_t view_distance, const VxFrameConfig *cfg,
+                           uint32_t *d_color_dst, float *d_depth_dst, const VxStripeSync *sync);
 /* Device pointers of the last rendered frame: colour (u32) and depth (f32), rows x width. */
 VX_API int vx_framebuffer_device(VxContext *ctx, uint32_t **d_color, float **d_depth, int32_t *rows, int32_t *width);
 VX_API int vx_frame_stats(VxContext *ctx, VxFrameStats *out);

@@ -85,7 +85,23 @@ def _worker(rank, world, port, out_dir, n_dev):
                     comp.release(fno)
             ctx.synchronize()
             dist.barrier()
+        # steady state without a host round trip per frame: arrival wait + acknowledgement in one kernel on rank 0
+        comp.set_stripes(sharding.balanced_stripes(band, h, world))
+        for k in range(5):
+            fno = comp._next
+            comp._next = fno + 1
+            comp.render(batch, vp, cam.position, cfg, vd, fno)
+            if rank == 0:
+                comp.complete_and_release(fno)
+        ctx.synchronize()
+        dist.barrier()
         comp.check()
+        api.frame_stats(ctx)  # a hand-off timeout inside the raster kernel would surface here
+        if rank == 0:
+            last = comp._next - 1
+            assert np.array_equal(comp.frame_tensor(last, dev).cpu().numpy().view(np.uint32), oc)
+            assert np.array_equal(comp.depth_tensor(last, dev).cpu().numpy().view(np.uint32), od.view(np.uint32))
+        dist.barrier()
         comp.close()
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
         ex.close()
