@@ -145,6 +145,7 @@ PROTOTYPES = {
     "vx_render_frame_into": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, C.POINTER(VxFrameConfig), _P, _P]),
     "vx_framebuffer_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I), C.POINTER(_I)]),
     "vx_frame_stats": (C.c_int, [_P, C.POINTER(VxFrameStats)]),
+    "vx_frame_counters": (C.c_int, [_P, _P]),
     "vx_frame_kernel_times": (C.c_int, [_P, _P]),
     "vx_frame_trace": (C.c_int, [_P, _P, _I, C.POINTER(_I)]),
     "vx_frame_setup_trace": (C.c_int, [_P, _P, _I, C.POINTER(_I)]),

@@ -385,6 +385,11 @@ VX_API int vx_render_frame_stripe(VxContext *ctx, const VxMeshBatch *batch, cons
 /* Device pointers of the last rendered frame: colour (u32) and depth (f32), rows x width. */
 VX_API int vx_framebuffer_device(VxContext *ctx, uint32_t **d_color, float **d_depth, int32_t *rows, int32_t *width);
 VX_API int vx_frame_stats(VxContext *ctx, VxFrameStats *out);
+/* Diagnostics: the raw 32-word control block of the last frame -- [0] survivors, [1] quads, [2] triangles kept, [3] bin
+ * entries, [4] overflow bits, [5] fullest bin, [6] big triangles (bounding box over more than 64 tiles), [7] setup units,
+ * [8] meshes culled by the occlusion pass, [9] raster work items, [12] items the plan wanted, [13] second near-clip
+ * pieces, [16..24] items per plan class, [25] raster CTAs that finished. */
+VX_API int vx_frame_counters(VxContext *ctx, uint32_t out[32]);
 /* CUDA-event durations (ms) of the last frame rendered with profile_kernels != 0:
  * [0] cull, [1] rank + project/clip/setup + binning, [2] unused (0), [3] work-item plan + span raster + write-out. */
 VX_API int vx_frame_kernel_times(VxContext *ctx, float ms_out[4]);

@@ -83,6 +83,9 @@ for i in slow:
 last = so[so[:, 10] > 0]
 if last.shape[0]:
     print(f"setup plan: start {(last[0, 5] - b0) / 1000:.1f} loaded {(last[0, 10] - b0) / 1000:.1f} written {(last[0, 11] - b0) / 1000:.1f} end {(last[0, 6] - b0) / 1000:.1f} us;  raster first item starts {(base - b0) / 1000:.1f} us after the first setup CTA")
+cnt = np.zeros(32, dtype=np.uint32)
+ctx.check(ctx.lib.vx_frame_counters(ctx.handle, cnt.ctypes.data_as(C.c_void_p)))
+print("control block: big triangles", int(cnt[6]), "setup units", int(cnt[7]), "items per class (K=0 class last)", cnt[16:25].tolist(), "second clip pieces", int(cnt[13]))
 st = api.frame_stats(ctx)
 print("survivors", st.n_survivors, "tris", st.n_triangles, "entries", st.n_bin_entries, "max_bin", st.reserved[0], "items", st.reserved[1])
 batch.release()
