@@ -304,9 +304,11 @@ def run_cuda(args):
         if comp is None:
             api.render_frame_device(batch, vp, cam.position, cfg_async, VD, ctx)
         else:
-            comp.render(batch, vp, cam.position, cfg, VD, frame_no)  # hand-off fused into the raster kernel
-            if rank == 0:
-                comp.complete_and_release(frame_no)  # one kernel: every stripe of this frame has landed in GPU0's memory -> buffer free
+            # hand-off fused into the raster kernels: every rank's last CTA publishes its stripe, GPU0's last CTA waits for all
+            # of them and hands the buffer back -- three launches per rank and frame, none of them a hand-off kernel
+            fused = comp.render(batch, vp, cam.position, cfg, VD, frame_no, compose_release=frame_no if rank == 0 else None)
+            if rank == 0 and not fused:
+                comp.complete_and_release(frame_no)
         frame_no += 1
 
     # ---- warm-up ---------------------------------------------------------------------------------------------------
@@ -441,12 +443,12 @@ def run_cuda(args):
     #      ARGB frame into page-locked host memory -- every step; two frames in flight; wall clock, max over ranks ----------
     e2e_multi = None
     if comp is not None:
-        # three buffers: frame k is being composed while frame k - 1 leaves GPU0 over the copy engine (second stream) and its
-        # buffer is handed back one step later
+        # four buffers: frame k is being composed while frame k - 1 leaves GPU0 over the copy engine (second stream); a buffer
+        # is handed back two steps later, when its frame is known to be in host memory
         ctx.synchronize()
         barrier()
         comp.close()
-        comp = multigpu.StripeCompositor(ctx, W, H, rank, world_size, want_depth=False, n_buffers=3)
+        comp = multigpu.StripeCompositor(ctx, W, H, rank, world_size, want_depth=False, n_buffers=4)
         comp.set_stripes(stripes)
         host = [ctx.host_array((H, W), np.int32) for _ in range(2)] if rank == 0 else None
         host_t = [torch.from_numpy(hh) for hh in host] if rank == 0 else None
@@ -459,13 +461,15 @@ def run_cuda(args):
         def e2e_submit(j):
             k = e2e_no[0]
             e2e_no[0] += 1
-            comp.render(batch, vp, cam.position, cfg, VD, k)
+            # frame k - 2 is in host memory already (the host waited for it before submitting this one), so GPU0's raster kernel
+            # of frame k can hand that buffer back itself once every stripe of frame k has arrived
+            fused = comp.render(batch, vp, cam.position, cfg, VD, k, compose_release=(k - 2 if k >= 2 else -1) if rank == 0 else None)
             if rank == 0:
-                if k >= 1:  # frame k - 1 has left GPU0 (stream order): its buffer is handed back with this frame's arrival wait
-                    stream.wait_event(copied[(j - 1) & 1])
-                    comp.complete_and_release(k, k - 1)
-                else:
-                    comp.complete(k)
+                if not fused:
+                    if k >= 2:
+                        comp.complete_and_release(k, k - 2)
+                    else:
+                        comp.complete(k)
                 composed[j & 1].record(stream)
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(composed[j & 1])
@@ -492,9 +496,6 @@ def run_cuda(args):
         el = time.perf_counter() - t0
         barrier()
         e2e_multi = ne2e / max_over_ranks(el)
-        if rank == 0:
-            stream.wait_event(copied[(ne2e - 1) & 1])
-            comp.release(e2e_no[0] - 1)
         ctx.synchronize()
         comp.check()
         if rank == 0:
@@ -592,9 +593,9 @@ def run_cuda(args):
     else:
         e2e_val = e2e_multi
         e2e_note = ("per step every rank gets VP + camera + config and renders its stripe (vx_render_frame_into) straight into GPU0's frame over "
-                    "NVLink; GPU0 waits for the arrival flags and sends the composed ARGB frame to page-locked host memory over the copy engine "
-                    "(second stream), the buffer is acknowledged one step later (three buffers); two frames in flight on the host; wall clock "
-                    "between barriers, max over ranks")
+                    "NVLink; GPU0's raster kernel waits for the arrival words, the composed ARGB frame goes to page-locked host memory over the copy "
+                    "engine (second stream), a buffer is acknowledged two steps later (four buffers); two frames in flight on the host; wall "
+                    "clock between barriers, max over ranks")
 
     # ---- second BASELINE metric: chunks meshed / s (whole-world remesh sweep of the Varied chunks, inputs resident) ----
     d_vox = torch.from_numpy(v).to(dev)
@@ -849,8 +850,8 @@ def bench_cfg5(torch, api, multigpu, sharding, ctx, stream, dev, rank, world_siz
         kk = [0]
 
         def step():
-            comp5.render(batch5, vp5, cam5.position, c5, VD5, kk[0])
-            if rank == 0:
+            fused = comp5.render(batch5, vp5, cam5.position, c5, VD5, kk[0], compose_release=kk[0] if rank == 0 else None)
+            if rank == 0 and not fused:
                 comp5.complete_and_release(kk[0])
             kk[0] += 1
 

@@ -120,8 +120,13 @@ class StripeCompositor:
         return self.color_ptr(frame_no) + self.frame_bytes if self.want_depth else 0
 
     # ---- per frame --------------------------------------------------------------------------------------------
-    def render(self, batch: api.MeshBatch, view_proj, camera_position, cfg, view_distance: int, frame_no: int):
-        """Enqueue this rank's stripe of frame `frame_no` (asynchronous; cfg is copied with the stripe filled in)."""
+    def render(self, batch: api.MeshBatch, view_proj, camera_position, cfg, view_distance: int, frame_no: int,
+               compose_release: Optional[int] = None):
+        """Enqueue this rank's stripe of frame `frame_no` (asynchronous; cfg is copied with the stripe filled in).
+        compose_release (dst only, needs a stripe with rows): fold the per-frame bookkeeping of the composing GPU into the
+        raster kernel as well -- its last CTA waits for every rank's arrival word of this frame and then hands the buffer of
+        frame `compose_release` back (use frame_no when nothing reads the frame on the host, an older frame otherwise).
+        Returns True when that was done (else call complete() / release() or complete_and_release())."""
         ctx, lib, h = self.ctx, self.ctx.lib, self.ctx.handle
         y0, rows = self.stripes[self.rank]
         arrive = self.arrive + 4 * FLAG_STRIDE_WORDS * self.rank
@@ -134,16 +139,26 @@ class StripeCompositor:
             off = y0 * self.W * 4
             sync = VxStripeSync(self.ack_local.value if wait_needed else None, (frame_no - self.n_buffers + 1) & 0xFFFFFFFF if wait_needed else 0,
                                 arrive, (frame_no + 1) & 0xFFFFFFFF, self.timeout_us)
+            fused = compose_release is not None and self.rank == self.dst
+            if fused:
+                self._rel_table = (C.c_void_p * self.world)(*self.acks)
+                sync.n_arrive, sync.arrive_stride_words, sync.d_arrive_flags = self.world, FLAG_STRIDE_WORDS, self.arrive
+                sync.arrive_value = (frame_no + 1) & 0xFFFFFFFF
+                sync.release_value = (compose_release + 1) & 0xFFFFFFFF if compose_release >= 0 else 0
+                sync.n_release = self.world if compose_release >= 0 else 0
+                sync.release_flags = C.cast(self._rel_table, C.c_void_p)
             vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
             cam = np.ascontiguousarray(camera_position, dtype=np.float32).reshape(3)
             ctx.check(lib.vx_render_frame_stripe(h, batch.handle, None, -1, api._p(vp), api._p(cam), int(view_distance), C.byref(c),
                                                  C.c_void_p(self.color_ptr(frame_no) + off),
                                                  C.c_void_p(self.depth_ptr(frame_no) + off) if self.want_depth else None, C.byref(sync)))
-        else:  # a rank without rows only reports in
-            if wait_needed:
-                ctx.check(lib.vx_wait_flags(h, self.ack_local, 1, 1, frame_no - self.n_buffers + 1, self.timeout_us))
-            flag = (C.c_void_p * 1)(arrive)
-            ctx.check(lib.vx_signal_flags(h, flag, 1, frame_no + 1))
+            return fused
+        # a rank without rows only reports in
+        if wait_needed:
+            ctx.check(lib.vx_wait_flags(h, self.ack_local, 1, 1, frame_no - self.n_buffers + 1, self.timeout_us))
+        flag = (C.c_void_p * 1)(arrive)
+        ctx.check(lib.vx_signal_flags(h, flag, 1, frame_no + 1))
+        return False
 
     def complete(self, frame_no: int):
         """dst only: enqueue the wait for every rank's stripe of `frame_no`; later work on the stream sees the frame."""

@@ -93,6 +93,12 @@ def _worker(rank, world, port, out_dir, n_dev):
             comp.render(batch, vp, cam.position, cfg, vd, fno)
             if rank == 0:
                 comp.complete_and_release(fno)
+        # ... and with the composing GPU's bookkeeping folded into its raster kernel (no hand-off kernel at all)
+        for k in range(5):
+            fno = comp._next
+            comp._next = fno + 1
+            fused = comp.render(batch, vp, cam.position, cfg, vd, fno, compose_release=fno if rank == 0 else None)
+            assert fused == (rank == 0)
         ctx.synchronize()
         dist.barrier()
         comp.check()
