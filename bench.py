@@ -9,8 +9,9 @@ quad + span rasterization with depth buffer and textured shading -- of the seede
 lattice chunks, the Varied ones meshed with their neighbours), camera (0,10,20) looking down -Z, meshes cached on the
 device exactly as the reference caches them between frames (main.rs:225-280).  A "step" is one frame.
 
-One JSON line on stdout (rank 0).  `value` = device-resident frames/s (CUDA events on the launching stream, L2 flushed
-between timed frames); `e2e` = the same frame through the public host API (VP + camera uploaded, ARGB frame read back
+One JSON line on stdout (rank 0).  `value` = device-resident frames/s with `--lanes` frames in flight (api.FrameLanes: one
+context -- stream + frame scratch -- per lane; the timed frames go out in groups of one frame per lane, every group starts
+behind an L2 flush and is timed with CUDA events from the end of the flush to the last lane's end); `e2e` = the same frame through the public host API (VP + camera uploaded, ARGB frame read back
 into pinned host memory, every step); `roofline` describes the dominant kernel; `cpu_baseline` is the C restatement of
 the reference CPU path timed on this box's host cores; `extra` carries the second metric of BASELINE.json (chunks
 meshed per second) and the per-kernel split.
@@ -135,7 +136,8 @@ def workload_config(n_gpus: int, sc, total_quads: int):
         "resolution": [W, H], "view_distance": VD,
         "chunks": int(sc["pos"].shape[0]), "varied_chunks": int(sc["p"].shape[0]), "total_quads": int(total_quads),
         "camera": "(0,10,20) yaw 0 pitch 0 fov 70",
-        "l2": "CUDA arm: L2 flushed between timed frames (256 MiB device write outside the timed events); CPU arm: not applicable",
+        "l2": "CUDA arm: L2 flushed (256 MiB device write, outside the timed events) before every timed group of frames -- one frame per "
+              "lane, all of them start cold; CPU arm: not applicable",
         "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} GPUs: work-balanced screen stripes, each rank's raster kernel stores its rows into the "
                                                    "composed frame in GPU0's memory over NVLink (CUDA IPC peer mapping, no collective)",
     }
@@ -239,8 +241,11 @@ def run_cuda(args):
     vp = cam.view_projection()
     ctx = api.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    L = max(1, args.lanes)
+    lanes = api.FrameLanes(local_rank, L, first=ctx)  # lane 0 is ctx
+    lane_streams = [torch.cuda.ExternalStream(c.stream, device=dev) for c in lanes.ctxs]
     n_lattice, n_varied = int(pos.shape[0]), int(p.shape[0])
-    extra = {}
+    extra = {"lanes": L}
 
     def barrier():
         if dist is not None:
@@ -285,73 +290,112 @@ def run_cuda(args):
     cfg_async = api.VxFrameConfig.from_buffer_copy(cfg)
     cfg_async.async_submit = 1
 
-    # ---- one synchronous full frame on every rank: sizes the scratch, gives the per-tile-row work for the stripe split ----
-    api.render_frame_device(batch, vp, cam.position, cfg, VD, ctx)
+    # ---- one synchronous full frame on every rank and lane: sizes the scratch, gives the per-tile-row work for the stripe split ----
+    for c in lanes.ctxs:
+        api.render_frame_device(batch, vp, cam.position, cfg, VD, c)
     st_full = api.frame_stats(ctx)
     comp = None
+    comps = None
     stripes = [(0, H)]
-    frame_no = 0
+    lane_frame_no = [0] * L
     if world_size > 1:
         band = api.frame_bin_counts(ctx).sum(axis=1).astype(np.float64)  # triangles binned per 8-row band of the full frame
         holder = [sharding.balanced_stripes(band, H, world_size, band=8, row_cost=float(band.sum()) / (4.0 * H))] if rank == 0 else [None]
         dist.broadcast_object_list(holder, src=0)
         stripes = [tuple(x) for x in holder[0]]
-        comp = multigpu.StripeCompositor(ctx, W, H, rank, world_size, want_depth=True)
-        comp.set_stripes(stripes)
+        # one compositor (composite buffers + flag words) per lane: a lane is an in-order sequence of frames of its own
+        comps = [multigpu.StripeCompositor(c, W, H, rank, world_size, want_depth=True) for c in lanes.ctxs]
+        for cp in comps:
+            cp.set_stripes(stripes)
+        comp = comps[0]
 
-    def step_device():
-        nonlocal frame_no
-        if comp is None:
-            api.render_frame_device(batch, vp, cam.position, cfg_async, VD, ctx)
+    def step_device(l: int = 0):
+        if comps is None:
+            api.render_frame_device(batch, vp, cam.position, cfg_async, VD, lanes[l])
         else:
             # hand-off fused into the raster kernels: every rank's last CTA publishes its stripe, GPU0's last CTA waits for all
             # of them and hands the buffer back -- three launches per rank and frame, none of them a hand-off kernel
-            fused = comp.render(batch, vp, cam.position, cfg, VD, frame_no, compose_release=frame_no if rank == 0 else None)
+            k = lane_frame_no[l]
+            fused = comps[l].render(batch, vp, cam.position, cfg, VD, k, compose_release=k if rank == 0 else None)
             if rank == 0 and not fused:
-                comp.complete_and_release(frame_no)
-        frame_no += 1
+                comps[l].complete_and_release(k)
+        lane_frame_no[l] += 1
+
+    def check_lanes():
+        lanes.synchronize()
+        for cp in comps or []:
+            cp.check()
+        for c in lanes.ctxs:
+            api.frame_stats(c)  # surfaces an overflow of an async frame, if any
+
+    def timed_groups(n_frames: int, n_lanes: int):
+        """n_frames frames in groups of one frame per lane; every group starts behind an L2 flush.  Device ms, summed over the
+        groups: from the end of the flush to the end of the group's last frame."""
+        groups = []
+        done = 0
+        while done < n_frames:
+            g = min(n_lanes, n_frames - done)
+            flush_l2()
+            f_ev = torch.cuda.Event(enable_timing=True)
+            f_ev.record(lane_streams[0])
+            ends = []
+            for l in range(g):
+                if l:
+                    lane_streams[l].wait_event(f_ev)
+                step_device(l)
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(lane_streams[l])
+                ends.append(e)
+            for l in range(1, g):
+                lane_streams[0].wait_event(ends[l])  # the next flush starts when every lane is done
+            groups.append((f_ev, ends))
+            done += g
+        torch.cuda.synchronize()
+        return sum(max(f_ev.elapsed_time(e) for e in ends) for f_ev, ends in groups)
 
     # ---- warm-up ---------------------------------------------------------------------------------------------------
     Wm = max(3, args.warmup)
     for _ in range(Wm):
-        step_device()
-    ctx.synchronize()
-    if comp is not None:
-        comp.check()
-    api.frame_stats(ctx)
+        for l in range(L):
+            step_device(l)
+    check_lanes()
     launches_per_frame = None
 
-    # ---- timed region: exactly K frames, CUDA events on the launching stream, L2 flushed between frames ---------
+    # ---- timed region: exactly K frames, L in flight; CUDA events on the launching streams, L2 flushed before every group ----
     sampler = ClockSampler(local_rank)
     barrier()
     torch.cuda.synchronize()
     sampler.start()
     K = max(1, args.steps)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    l0 = ctx.launch_count
-    for i in range(K):
-        flush_l2()
-        starts[i].record(stream)
-        step_device()
-        ends[i].record(stream)
-    torch.cuda.synchronize()
-    l1 = ctx.launch_count
+    l0 = lanes.launch_count
+    total_ms = timed_groups(K, L)
+    l1 = lanes.launch_count
     launches_per_frame = (l1 - l0) / K
-    if comp is not None:
-        comp.check()
+    for cp in comps or []:
+        cp.check()
     # keep the same load running until the sampler has seen >= 1.5 s of it (the timed frames are ~tens of microseconds)
     t_probe = time.perf_counter()
     while time.perf_counter() - t_probe < 1.5:
-        for _ in range(50):  # this rank's frames only: a time-based loop must not contain cross-rank waits
-            api.render_frame_device(batch, vp, cam.position, cfg_async, VD, ctx)
-        ctx.synchronize()
+        for i in range(60):  # this rank's frames only: a time-based loop must not contain cross-rank waits
+            api.render_frame_device(batch, vp, cam.position, cfg_async, VD, lanes[i % L])
+        lanes.synchronize()
     clocks = sampler.stop()
     barrier()
     torch.cuda.synchronize()
-    ms_per_step = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(starts, ends))) / K
+    ms_per_step = max_over_ranks(total_ms) / K
     fps = 1000.0 / ms_per_step
-    api.frame_stats(ctx)  # surfaces an overflow of an async frame, if any
+    check_lanes()
+    # the same frames one at a time (one lane, L2 flushed before each): the latency of a frame
+    if L > 1:
+        n_alone = min(K, 100)
+        barrier()
+        alone_ms = max_over_ranks(timed_groups(n_alone, 1)) / n_alone
+        check_lanes()
+    else:
+        alone_ms = ms_per_step
+    extra["frame_alone_ms"] = alone_ms
+    extra["frames_per_sec_one_frame_in_flight"] = 1000.0 / alone_ms
+    frame_no = lane_frame_no[0]
 
     # ---- N > 1 guards (outside the timed region): the composed frame equals this GPU's own full frame, bit for bit;
     #      the assembled batch equals a locally meshed one ------------------------------------------------------------
@@ -359,6 +403,7 @@ def run_cuda(args):
         k = frame_no
         comp.render(batch, vp, cam.position, cfg, VD, k)
         frame_no += 1
+        lane_frame_no[0] = frame_no
         if rank == 0:
             comp.complete(k)
             ctx.synchronize()
@@ -442,64 +487,80 @@ def run_cuda(args):
     # ---- e2e at N > 1: VP + camera + config in on every rank, stripes stored into GPU0's frame, GPU0 copies the composed
     #      ARGB frame into page-locked host memory -- every step; two frames in flight; wall clock, max over ranks ----------
     e2e_multi = None
-    if comp is not None:
-        # four buffers: frame k is being composed while frame k - 1 leaves GPU0 over the copy engine (second stream); a buffer
-        # is handed back two steps later, when its frame is known to be in host memory
-        ctx.synchronize()
+    if comps is not None:
+        # per lane four composite buffers: frame k of a lane is being composed while its frame k - 1 leaves GPU0 over the copy
+        # engine (second stream); a buffer is handed back two lane-steps later, when its frame is known to be in host memory
+        lanes.synchronize()
         barrier()
-        comp.close()
-        comp = multigpu.StripeCompositor(ctx, W, H, rank, world_size, want_depth=False, n_buffers=4)
-        comp.set_stripes(stripes)
-        host = [ctx.host_array((H, W), np.int32) for _ in range(2)] if rank == 0 else None
-        host_t = [torch.from_numpy(hh) for hh in host] if rank == 0 else None
-        copy_stream = torch.cuda.Stream(device=dev)
-        composed = [torch.cuda.Event() for _ in range(2)]
-        copied = [torch.cuda.Event() for _ in range(2)]
-        submitted = [torch.cuda.Event() for _ in range(2)]
-        e2e_no = [0]
+        for cp in comps:
+            cp.close()
+        comps = [multigpu.StripeCompositor(c, W, H, rank, world_size, want_depth=False, n_buffers=4) for c in lanes.ctxs]
+        for cp in comps:
+            cp.set_stripes(stripes)
+        comp = comps[0]
+        host = [[ctx.host_array((H, W), np.int32) for _ in range(2)] for _ in range(L)] if rank == 0 else None
+        host_t = [[torch.from_numpy(hh) for hh in hl] for hl in host] if rank == 0 else None
+        copy_streams = [torch.cuda.Stream(device=dev) for _ in range(L)]
+        composed = [[torch.cuda.Event() for _ in range(2)] for _ in range(L)]
+        copied = [[torch.cuda.Event() for _ in range(2)] for _ in range(L)]
+        submitted = [[torch.cuda.Event() for _ in range(2)] for _ in range(L)]
+        lane_k = [0] * L
+        D = L + 1  # frames in flight on the host (at most two per lane)
 
         def e2e_submit(j):
-            k = e2e_no[0]
-            e2e_no[0] += 1
-            # frame k - 2 is in host memory already (the host waited for it before submitting this one), so GPU0's raster kernel
-            # of frame k can hand that buffer back itself once every stripe of frame k has arrived
-            fused = comp.render(batch, vp, cam.position, cfg, VD, k, compose_release=(k - 2 if k >= 2 else -1) if rank == 0 else None)
+            l = j % L
+            k = lane_k[l]
+            lane_k[l] += 1
+            # the lane's frame k - 2 is in host memory already (the host waited for it before submitting this one), so GPU0's
+            # raster kernel of frame k can hand that buffer back itself once every stripe of frame k has arrived
+            fused = comps[l].render(batch, vp, cam.position, cfg, VD, k, compose_release=(k - 2 if k >= 2 else -1) if rank == 0 else None)
             if rank == 0:
                 if not fused:
                     if k >= 2:
-                        comp.complete_and_release(k, k - 2)
+                        comps[l].complete_and_release(k, k - 2)
                     else:
-                        comp.complete(k)
-                composed[j & 1].record(stream)
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(composed[j & 1])
-                    host_t[j & 1].copy_(comp.frame_tensor(k, dev), non_blocking=True)
-                    copied[j & 1].record(copy_stream)
-            submitted[j & 1].record(stream)
+                        comps[l].complete(k)
+                composed[l][k & 1].record(lane_streams[l])
+                with torch.cuda.stream(copy_streams[l]):
+                    copy_streams[l].wait_event(composed[l][k & 1])
+                    host_t[l][k & 1].copy_(comps[l].frame_tensor(k, dev), non_blocking=True)
+                    copied[l][k & 1].record(copy_streams[l])
+            submitted[l][k & 1].record(lane_streams[l])
 
         def e2e_wait(j):
-            (copied if rank == 0 else submitted)[j & 1].synchronize()
+            l, k = j % L, j // L
+            (copied if rank == 0 else submitted)[l][k & 1].synchronize()
 
-        for j in range(4):
-            e2e_submit(j)
-            if j >= 1:
-                e2e_wait(j - 1)
-        e2e_wait(3)
+        def e2e_run(n):
+            for j in range(n):
+                e2e_submit(j)
+                if j >= D - 1:
+                    e2e_wait(j - (D - 1))  # rank 0: that frame is complete in host memory
+            for j in range(max(0, n - (D - 1)), n):
+                e2e_wait(j)
+
+        e2e_run(4 * L)
+        for l in range(L):  # e2e_wait derives a lane's frame number from the run-local index: keep both in step
+            assert lane_k[l] % 2 == 0
         ne2e = max(20, min(K, 200))
+        ne2e -= ne2e % (2 * L)
+        base_k = list(lane_k)
+
+        def e2e_wait(j):  # noqa: F811 -- the timed run continues the lanes' frame numbers
+            l, k = j % L, base_k[j % L] + j // L
+            (copied if rank == 0 else submitted)[l][k & 1].synchronize()
+
         barrier()
         t0 = time.perf_counter()
-        e2e_submit(0)
-        for j in range(1, ne2e):
-            e2e_submit(j)
-            e2e_wait(j - 1)  # rank 0: frame j - 1 is complete in host memory
-        e2e_wait(ne2e - 1)
+        e2e_run(ne2e)
         el = time.perf_counter() - t0
         barrier()
         e2e_multi = ne2e / max_over_ranks(el)
-        ctx.synchronize()
-        comp.check()
+        lanes.synchronize()
+        for cp in comps:
+            cp.check()
         if rank == 0:
-            extra["e2e_frames_identical"] = bool(torch.equal(host_t[0], host_t[1]))
+            extra["e2e_frames_identical"] = bool(all(torch.equal(host_t[0][0], host_t[l][b]) for l in range(L) for b in range(2)))
 
     # ---- BASELINE cfg 5 (3840x2160, view distance 32): 1 GPU, and at N > 1 the stripe frame with / without the composite ---
     cfg5 = None
@@ -510,8 +571,9 @@ def run_cuda(args):
         log("cfg5 failed:", repr(e))
 
     if rank != 0:
-        if comp is not None:
-            comp.close()
+        for cp in comps or []:
+            cp.close()
+        lanes.close()
         return teardown(torch, dist, ctx, [batch] if exchange is None else [], exchange)
 
     # =============================== rank 0 only from here ===============================================================
@@ -559,7 +621,7 @@ def run_cuda(args):
     d2h = W * H * 4 + 4 * n_lattice + 64  # frame + draw order + control block
     e2e_val, e2e_sync, e2e_note = None, None, None
     if world_size == 1:
-        loop = api.FrameLoop(batch, cfg, view_distance=VD, want_depth=False, ctx=ctx)
+        loop = api.FrameLoop(batch, cfg, view_distance=VD, want_depth=False, ctx=ctx, lanes=L)
         for _ in range(3):
             c_sync, _, s_sync = loop.render(vp, cam.position)
         ref_frame, ref_order = c_sync.copy(), s_sync.copy()
@@ -569,33 +631,42 @@ def run_cuda(args):
         for _ in range(ne2e):
             loop.render(vp, cam.position)
         e2e_sync = ne2e / (time.perf_counter() - t0)
-        for _ in range(2):
-            loop.wait(loop.submit(vp, cam.position))
-        ok = True
+        D = L + 1  # frames in flight on the host
+
+        def e2e_run(n):
+            ok_, pend = True, []
+            for _ in range(n):
+                pend.append(loop.submit(vp, cam.position))
+                if len(pend) >= D:
+                    c_, _, s_ = loop.wait(pend.pop(0))  # that frame is complete in host memory here
+                    ok_ = ok_ and c_[H // 2, W // 2] == ref_frame[H // 2, W // 2]
+            while pend:
+                c_, _, s_ = loop.wait(pend.pop(0))
+                ok_ = ok_ and bool(np.array_equal(c_, ref_frame) and np.array_equal(s_, ref_order))  # the last D frames in full
+            return ok_
+
+        e2e_run(4 * L)
         t0 = time.perf_counter()
-        prev = loop.submit(vp, cam.position)
-        for _ in range(1, ne2e):
-            nxt = loop.submit(vp, cam.position)
-            c_, _, s_ = loop.wait(prev)  # frame `prev` is complete in host memory here
-            prev = nxt
-        c_, _, s_ = loop.wait(prev)
+        ok = e2e_run(ne2e)
         e2e_val = ne2e / (time.perf_counter() - t0)
-        ok = bool(np.array_equal(c_, ref_frame) and np.array_equal(s_, ref_order))
         extra["e2e_pipelined_frames_identical_to_synchronous"] = ok
         extra["e2e_synchronous_frames_per_s"] = e2e_sync
+        extra["e2e_d2h_GBps"] = e2e_val * d2h / 1e9
         if not ok:
             e2e_val = e2e_sync
-        e2e_note = ("api.FrameLoop.submit / wait -> vx_render_frame_begin / _end: VP + camera + config in; the ARGB frame (written over PCIe by the "
-                    "raster kernel itself into device-mapped page-locked memory, no staging copy) and the draw order land in host memory every "
-                    "step; two frames in flight (frame k+1 is enqueued before the host waits for frame k); colour only -- the depth plane is "
-                    "frame-internal (the reference presents color_buffer only, main.rs:320-322); extra.e2e_synchronous_frames_per_s = one "
-                    "blocking vx_render_frame per step")
+        e2e_note = (f"api.FrameLoop(lanes={L}).submit / wait -> vx_render_frame_begin / _end: VP + camera + config in; the frame is rendered into a "
+                    "device buffer of its in-flight slot and leaves over the copy engine on a second stream, the ARGB frame, the draw order and "
+                    f"the frame's control block land in page-locked host memory every step; {L} lanes, {L + 1} frames in flight on the host (the "
+                    "oldest is waited for before another is enqueued); the loop is bound by the PCIe transfer of the frame "
+                    "(extra.e2e_d2h_GBps); colour only -- the depth plane is frame-internal (the reference presents color_buffer only, "
+                    "main.rs:320-322); extra.e2e_synchronous_frames_per_s = one blocking vx_render_frame per step")
     else:
         e2e_val = e2e_multi
-        e2e_note = ("per step every rank gets VP + camera + config and renders its stripe (vx_render_frame_into) straight into GPU0's frame over "
+        extra["e2e_d2h_GBps"] = e2e_val * d2h / 1e9
+        e2e_note = ("per step every rank gets VP + camera + config and renders its stripe (vx_render_frame_stripe) straight into GPU0's frame over "
                     "NVLink; GPU0's raster kernel waits for the arrival words, the composed ARGB frame goes to page-locked host memory over the copy "
-                    "engine (second stream), a buffer is acknowledged two steps later (four buffers); two frames in flight on the host; wall "
-                    "clock between barriers, max over ranks")
+                    f"engine (second stream), a buffer is acknowledged two lane-steps later (four buffers per lane); {L} lanes, {L + 1} frames in "
+                    "flight on the host; wall clock between barriers, max over ranks")
 
     # ---- second BASELINE metric: chunks meshed / s (whole-world remesh sweep of the Varied chunks, inputs resident) ----
     d_vox = torch.from_numpy(v).to(dev)
@@ -770,8 +841,9 @@ def run_cuda(args):
     if world_size == 1:
         del loop
     vbatch.release()
-    if comp is not None:
-        comp.close()
+    for cp in comps or []:
+        cp.close()
+    lanes.close()
     return teardown(torch, dist, ctx, [batch] if exchange is None else [], exchange)
 
 
@@ -984,6 +1056,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--lanes", type=int, default=3, help="frames in flight on each GPU (api.FrameLanes)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

