@@ -505,7 +505,7 @@ def run_cuda(args):
         copied = [[torch.cuda.Event() for _ in range(2)] for _ in range(L)]
         submitted = [[torch.cuda.Event() for _ in range(2)] for _ in range(L)]
         lane_k = [0] * L
-        D = L + 1  # frames in flight on the host (at most two per lane)
+        D = max(1, min(2 * L, args.e2e_depth if args.e2e_depth > 0 else L))  # frames in flight on the host (at most two per lane)
 
         def e2e_submit(j):
             l = j % L
@@ -631,7 +631,8 @@ def run_cuda(args):
         for _ in range(ne2e):
             loop.render(vp, cam.position)
         e2e_sync = ne2e / (time.perf_counter() - t0)
-        D = L + 1  # frames in flight on the host
+        D = max(1, min(2 * L, args.e2e_depth if args.e2e_depth > 0 else L))  # frames in flight on the host (measured: deeper queues only add latency)
+        extra["e2e_frames_in_flight"] = D
 
         def e2e_run(n):
             ok_, pend = True, []
@@ -656,7 +657,7 @@ def run_cuda(args):
             e2e_val = e2e_sync
         e2e_note = (f"api.FrameLoop(lanes={L}).submit / wait -> vx_render_frame_begin / _end: VP + camera + config in; the frame is rendered into a "
                     "device buffer of its in-flight slot and leaves over the copy engine on a second stream, the ARGB frame, the draw order and "
-                    f"the frame's control block land in page-locked host memory every step; {L} lanes, {L + 1} frames in flight on the host (the "
+                    f"the frame's control block land in page-locked host memory every step; {L} lanes, {D} frames in flight on the host (the "
                     "oldest is waited for before another is enqueued); the loop is bound by the PCIe transfer of the frame "
                     "(extra.e2e_d2h_GBps); colour only -- the depth plane is frame-internal (the reference presents color_buffer only, "
                     "main.rs:320-322); extra.e2e_synchronous_frames_per_s = one blocking vx_render_frame per step")
@@ -665,7 +666,7 @@ def run_cuda(args):
         extra["e2e_d2h_GBps"] = e2e_val * d2h / 1e9
         e2e_note = ("per step every rank gets VP + camera + config and renders its stripe (vx_render_frame_stripe) straight into GPU0's frame over "
                     "NVLink; GPU0's raster kernel waits for the arrival words, the composed ARGB frame goes to page-locked host memory over the copy "
-                    f"engine (second stream), a buffer is acknowledged two lane-steps later (four buffers per lane); {L} lanes, {L + 1} frames in "
+                    f"engine (second stream), a buffer is acknowledged two lane-steps later (four buffers per lane); {L} lanes, {min(2 * L, args.e2e_depth if args.e2e_depth > 0 else L)} frames in "
                     "flight on the host; wall clock between barriers, max over ranks")
 
     # ---- second BASELINE metric: chunks meshed / s (whole-world remesh sweep of the Varied chunks, inputs resident) ----
@@ -1057,6 +1058,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--lanes", type=int, default=3, help="frames in flight on each GPU (api.FrameLanes)")
+    ap.add_argument("--e2e-depth", type=int, default=0, help="frames in flight on the host in the e2e loop (default lanes, at most 2 * lanes)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

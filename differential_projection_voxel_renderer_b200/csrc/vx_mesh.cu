@@ -54,6 +54,7 @@ struct MeshSmem {
     uint32_t faceRows[6], faceCols[6], faceSlices[6];
     uint32_t occ[3]; // bit s: slice s along x / y / z holds a solid voxel
     uint32_t base, total, overflow, pool_used, slow;
+    int32_t next_oi; // the chunk this CTA meshes next (fetched from the batch's work counter while the current one is in flight)
 };
 
 // 4 voxels (one per byte, values 0..3) -> 4 bits, voxel k -> bit k.  bit = 0 or 1 selects the type bit.
@@ -153,7 +154,7 @@ struct ChunkArgs {
     uint32_t *quad_base, *quad_count, *slice_offsets;
     int32_t *face_aabb;
     uint8_t *has_mesh;
-    unsigned long long *cursor; // [0] quad cursor, [1] mesh counter, [2] overflow flag
+    unsigned long long *cursor; // [0] quad cursor, [1] mesh counter, [2] overflow flag, [3] work counter (chunks handed out beyond the first wave)
 };
 
 // Neighbour solid planes.  First in load order: f=0/1 (+X/-X): i = y, bit z;  f=2/3 (+Y/-Y): i = z, bit x;
@@ -317,7 +318,15 @@ __global__ void __launch_bounds__(MESH_THREADS, VX_MESH_MIN_BLOCKS) mesh_chunks_
     __shared__ MeshSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int oi = blockIdx.x; oi < a.n_out; oi += gridDim.x) {
+    // Chunks are handed out dynamically: every CTA starts with chunk blockIdx.x and draws the following ones from a counter, so
+    // a CTA that got a light chunk (a few dozen quads) takes over work a static stride would have left to a CTA still busy
+    // with a heavy one (over a thousand).  The world sweep is ~1.1 resident waves of chunks: the second "wave" used to double
+    // its duration.  The draw is issued at the start of a chunk and read at its end (latency hidden behind the chunk).
+    int oi = blockIdx.x;
+    while (oi < a.n_out) {
+        __syncthreads(); // everybody is done with the previous chunk and has read next_oi
+        if (tid == 0) sm.next_oi = (int32_t)gridDim.x + (int32_t)atomicAdd(a.cursor + 3, 1ull);
+        do {
         const int chunk = a.subset ? a.subset[oi] : oi; // input chunk
         const int oo = a.out_by_chunk ? chunk : oi;     // where its outputs go
         uint32_t *so = a.slice_offsets + (size_t)oo * 198;
@@ -330,7 +339,7 @@ __global__ void __launch_bounds__(MESH_THREADS, VX_MESH_MIN_BLOCKS) mesh_chunks_
                 a.quad_count[oo] = 0;
                 a.has_mesh[oo] = 0;
             }
-            continue;
+            break;
         }
         // ---- stage 1: byte volume -> bit planes P[y][z] (bits x)
         const uint4 *src = reinterpret_cast<const uint4 *>(a.voxels + (size_t)chunk * VX_CHUNK_VOLUME);
@@ -464,6 +473,9 @@ __global__ void __launch_bounds__(MESH_THREADS, VX_MESH_MIN_BLOCKS) mesh_chunks_
                 process_units<1>(sm, a, tid); // rare: more quads than the pool holds
             }
         }
+        } while (0);
+        __syncthreads();
+        oi = sm.next_oi;
     }
 }
 
@@ -498,6 +510,7 @@ int run_mesher(VxContext *ctx, const uint8_t *d_vox, const int32_t *d_nb, const 
                int32_t n_sub = 0) {
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (!append) VX_CUDA(ctx, cudaMemsetAsync(b->cursor.ptr, 0, sizeof(unsigned long long) * 4, ctx->stream));
+        else VX_CUDA(ctx, cudaMemsetAsync(b->cursor.as<unsigned long long>() + 3, 0, sizeof(unsigned long long), ctx->stream)); // work counter
         ChunkArgs a;
         a.voxels = d_vox;
         a.neighbors = d_nb;
