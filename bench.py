@@ -289,6 +289,8 @@ def run_cuda(args):
     cfg = api.default_frame_config(W, H)
     cfg_async = api.VxFrameConfig.from_buffer_copy(cfg)
     cfg_async.async_submit = 1
+    cfg_lanes = api.VxFrameConfig.from_buffer_copy(cfg_async)  # frames that share the GPU: coarser raster work items
+    cfg_lanes.frames_in_flight = L
 
     # ---- one synchronous full frame on every rank and lane: sizes the scratch, gives the per-tile-row work for the stripe split ----
     for c in lanes.ctxs:
@@ -309,14 +311,18 @@ def run_cuda(args):
             cp.set_stripes(stripes)
         comp = comps[0]
 
-    def step_device(l: int = 0):
+    cfg_stripe_lanes = api.VxFrameConfig.from_buffer_copy(cfg)
+    cfg_stripe_lanes.frames_in_flight = L
+
+    def step_device(l: int = 0, in_flight: int = 1):
         if comps is None:
-            api.render_frame_device(batch, vp, cam.position, cfg_async, VD, lanes[l])
+            api.render_frame_device(batch, vp, cam.position, cfg_lanes if in_flight > 1 else cfg_async, VD, lanes[l])
         else:
             # hand-off fused into the raster kernels: every rank's last CTA publishes its stripe, GPU0's last CTA waits for all
             # of them and hands the buffer back -- three launches per rank and frame, none of them a hand-off kernel
             k = lane_frame_no[l]
-            fused = comps[l].render(batch, vp, cam.position, cfg, VD, k, compose_release=k if rank == 0 else None)
+            fused = comps[l].render(batch, vp, cam.position, cfg_stripe_lanes if in_flight > 1 else cfg, VD, k,
+                                    compose_release=k if rank == 0 else None)
             if rank == 0 and not fused:
                 comps[l].complete_and_release(k)
         lane_frame_no[l] += 1
@@ -342,7 +348,7 @@ def run_cuda(args):
             for l in range(g):
                 if l:
                     lane_streams[l].wait_event(f_ev)
-                step_device(l)
+                step_device(l, n_lanes)
                 e = torch.cuda.Event(enable_timing=True)
                 e.record(lane_streams[l])
                 ends.append(e)
@@ -357,7 +363,7 @@ def run_cuda(args):
     Wm = max(3, args.warmup)
     for _ in range(Wm):
         for l in range(L):
-            step_device(l)
+            step_device(l, L)
     check_lanes()
     launches_per_frame = None
 
@@ -377,7 +383,7 @@ def run_cuda(args):
     t_probe = time.perf_counter()
     while time.perf_counter() - t_probe < 1.5:
         for i in range(60):  # this rank's frames only: a time-based loop must not contain cross-rank waits
-            api.render_frame_device(batch, vp, cam.position, cfg_async, VD, lanes[i % L])
+            api.render_frame_device(batch, vp, cam.position, cfg_lanes, VD, lanes[i % L])
         lanes.synchronize()
     clocks = sampler.stop()
     barrier()
@@ -513,7 +519,7 @@ def run_cuda(args):
             lane_k[l] += 1
             # the lane's frame k - 2 is in host memory already (the host waited for it before submitting this one), so GPU0's
             # raster kernel of frame k can hand that buffer back itself once every stripe of frame k has arrived
-            fused = comps[l].render(batch, vp, cam.position, cfg, VD, k, compose_release=(k - 2 if k >= 2 else -1) if rank == 0 else None)
+            fused = comps[l].render(batch, vp, cam.position, cfg_stripe_lanes, VD, k, compose_release=(k - 2 if k >= 2 else -1) if rank == 0 else None)
             if rank == 0:
                 if not fused:
                     if k >= 2:

@@ -43,7 +43,7 @@ class VxFrameConfig(C.Structure):
                 ("differential_projection", C.c_int32), ("async_submit", C.c_int32),
                 ("profile_kernels", C.c_int32), ("macrotile", C.c_int32),
                 ("occlusion_culling", C.c_int32), ("occlusion_grid_w", C.c_int32), ("occlusion_grid_h", C.c_int32),
-                ("reserved", C.c_int32 * 1)]
+                ("frames_in_flight", C.c_int32)]
 
 
 class VxTerrainParams(C.Structure):

@@ -653,6 +653,12 @@ class FrameLoop:
         self._cam[:] = camera_position
         a = self._args
         k = self._n_submitted
+        if len(self.lanes) > 1:  # tell the library that this frame shares the GPU (coarser raster work items); cfg may have changed
+            if getattr(self, "_cfg_lanes", None) is None:
+                self._cfg_lanes = VxFrameConfig()
+            C.memmove(C.byref(self._cfg_lanes), C.byref(self.cfg), C.sizeof(VxFrameConfig))
+            self._cfg_lanes.frames_in_flight = len(self.lanes)
+            a = a[:7] + (C.byref(self._cfg_lanes),) + a[8:]
         li = k % len(self.lanes)
         lane = self.lanes[li]
         j = (k // len(self.lanes)) & 1

@@ -106,7 +106,11 @@ typedef struct {
      * frame (128 x 72, main.rs:46-47; at most 12288 cells).  Ignored by vx_render_mesh and in macrotile mode. */
     int32_t occlusion_culling;
     int32_t occlusion_grid_w, occlusion_grid_h;
-    int32_t reserved[1];
+    /* Hint: frames the caller keeps in flight on this device at the same time (contexts used as lanes, see
+     * vx_render_frame_begin); 0 or 1 = this frame has the GPU to itself.  It only changes how finely the raster work of a
+     * frame is cut (a frame that shares the GPU with others is cut coarser: fewer, larger work items = fewer instructions
+     * for the same pixels), never the result. */
+    int32_t frames_in_flight;
 } VxFrameConfig;
 
 typedef struct {
@@ -347,8 +351,13 @@ VX_API int vx_render_frame(VxContext *ctx, const VxMeshBatch *batch, const int32
  * (begin k+1 may precede end k), so each needs its own buffers, and the buffers must be page-locked memory
  * (vx_host_alloc): the frame is rendered into a device buffer of its in-flight slot and leaves through the copy engine
  * on a second stream, so the PCIe transfer of frame k runs beside the kernels of frame k+1 (steady-state period =
- * max(render, transfer)).  A frame whose scratch overflowed is re-rendered synchronously inside _end, so the result
- * is always the same as vx_render_frame's. */
+ * max(render, transfer)).  The frame's statistics and draw order are written into the slot by the frame's own kernels
+ * and travel with it, so the context's next frame never waits for a transfer.  A frame whose scratch overflowed is
+ * re-rendered synchronously inside _end, so the result is always the same as vx_render_frame's.
+ * Frames in flight ON THE DEVICE: contexts are independent (stream + frame scratch each), so a caller that deals its
+ * frames round-robin over L contexts of one device ("lanes") lets the kernels of different frames overlap -- one frame
+ * is three dependent latency-bound kernels and leaves most of the GPU idle; L = 3 raises the device's frame throughput
+ * by half.  Nothing else is needed: any batch can be rendered through any context of its device. */
 VX_API int vx_render_frame_begin(VxContext *ctx, const VxMeshBatch *batch, const int32_t *mesh_ids, int32_t n_meshes,
                           const float vp[16], const float cam_pos[3], int32_t view_distance, const VxFrameConfig *cfg,
                           uint32_t *color_out, float *depth_out, int32_t *ticket);
@@ -398,7 +407,8 @@ VX_API int vx_frame_stats(VxContext *ctx, VxFrameStats *out);
 /* Diagnostics: the raw 32-word control block of the last frame -- [0] survivors, [1] quads, [2] triangles kept, [3] bin
  * entries, [4] overflow bits, [5] fullest bin, [6] big triangles (bounding box over more than 64 tiles), [7] setup units,
  * [8] meshes culled by the occlusion pass, [9] raster work items, [12] items the plan wanted, [13] second near-clip
- * pieces, [16..24] items per plan class, [25] raster CTAs that finished. */
+ * pieces, [14] (triangle, row, column block) tasks binned, [16..24] items per plan class, [25] raster CTAs that
+ * finished. */
 VX_API int vx_frame_counters(VxContext *ctx, uint32_t out[32]);
 /* CUDA-event durations (ms) of the last frame rendered with profile_kernels != 0:
  * [0] cull, [1] rank + project/clip/setup + binning, [2] unused (0), [3] work-item plan + span raster + write-out. */

@@ -2,6 +2,7 @@
 scratch each), frames dealt round-robin, asynchronous submits.  Prints device throughput for L = 1, 2, 3.
    python tools/overlap_probe.py [W H VD]"""
 import os, sys, time
+import ctypes as C
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -25,11 +26,16 @@ for c in ctxs:
     c.synchronize()
 ref = api.framebuffer_device(ctxs[0])
 K = 600
-for L in (1, 2, 3, 1, 2):
+def cfg_for(L):
+    c = api.VxFrameConfig.from_buffer_copy(cfga)
+    c.frames_in_flight = L
+    return c
+for L in (1, 2, 3):
     torch.cuda.synchronize()
+    cl = cfg_for(L)
     t0 = time.perf_counter()
     for i in range(K):
-        api.render_frame_device(batch, vp, cam.position, cfga, VD, ctxs[i % L])
+        api.render_frame_device(batch, vp, cam.position, cl, VD, ctxs[i % L])
     t_sub = time.perf_counter() - t0
     torch.cuda.synchronize()
     t = time.perf_counter() - t0
@@ -39,7 +45,16 @@ for L in (1, 2, 3, 1, 2):
 # end of the flush to the last lane's end, per frame
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
 streams = [torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", 0)) for c in ctxs]
-for L in (1, 2, 3):
+for L in (1, 2, 3, 4):
+    if L > len(ctxs):
+        ctxs.append(api.Context(0))
+        api.render_frame_device(batch, vp, cam.position, cfg, VD, ctxs[-1])
+        streams.append(torch.cuda.ExternalStream(ctxs[-1].stream, device=torch.device("cuda", 0)))
+    cl = cfg_for(L)
+    for l in range(L):
+        for _ in range(3):
+            api.render_frame_device(batch, vp, cam.position, cl, VD, ctxs[l])
+    torch.cuda.synchronize()
     G = 200 // L
     tot = 0.0
     evs = []
@@ -51,7 +66,7 @@ for L in (1, 2, 3):
         for l in range(L):
             if l:
                 streams[l].wait_event(f_ev)
-            api.render_frame_device(batch, vp, cam.position, cfga, VD, ctxs[l])
+            api.render_frame_device(batch, vp, cam.position, cl, VD, ctxs[l])
             e = torch.cuda.Event(enable_timing=True); e.record(streams[l]); ends.append(e)
         for l in range(1, L):
             streams[0].wait_event(ends[l])  # the next flush starts when every lane is done
@@ -59,4 +74,6 @@ for L in (1, 2, 3):
     torch.cuda.synchronize()
     for f_ev, ends in evs:
         tot += max(f_ev.elapsed_time(e) for e in ends)
-    print(f"group mode lanes {L}: {tot / (G * L) * 1e3:.1f} us per frame ({G * L / tot * 1e3:.0f} frames/s), group {tot / G * 1e3:.1f} us")
+    cnt = (C.c_uint32 * 32)()
+    ctxs[0].check(ctxs[0].lib.vx_frame_counters(ctxs[0].handle, cnt))
+    print(f"group mode lanes {L}: {tot / (G * L) * 1e3:.1f} us per frame ({G * L / tot * 1e3:.0f} frames/s), group {tot / G * 1e3:.1f} us | tasks {cnt[14]} items {cnt[9]} entries {cnt[3]}")
