@@ -500,21 +500,23 @@ def run_cuda(args):
         barrier()
         for cp in comps:
             cp.close()
-        comps = [multigpu.StripeCompositor(c, W, H, rank, world_size, want_depth=False, n_buffers=4) for c in lanes.ctxs]
+        Lm = max(1, min(L, args.e2e_lanes))  # lanes of the e2e loop (PCIe-bound from three on)
+        extra["e2e_lanes"] = Lm
+        comps = [multigpu.StripeCompositor(c, W, H, rank, world_size, want_depth=False, n_buffers=4) for c in lanes.ctxs[:Lm]]
         for cp in comps:
             cp.set_stripes(stripes)
         comp = comps[0]
-        host = [[ctx.host_array((H, W), np.int32) for _ in range(2)] for _ in range(L)] if rank == 0 else None
+        host = [[ctx.host_array((H, W), np.int32) for _ in range(2)] for _ in range(Lm)] if rank == 0 else None
         host_t = [[torch.from_numpy(hh) for hh in hl] for hl in host] if rank == 0 else None
-        copy_streams = [torch.cuda.Stream(device=dev) for _ in range(L)]
-        composed = [[torch.cuda.Event() for _ in range(2)] for _ in range(L)]
-        copied = [[torch.cuda.Event() for _ in range(2)] for _ in range(L)]
-        submitted = [[torch.cuda.Event() for _ in range(2)] for _ in range(L)]
-        lane_k = [0] * L
-        D = max(1, min(2 * L, args.e2e_depth if args.e2e_depth > 0 else L))  # frames in flight on the host (at most two per lane)
+        copy_streams = [torch.cuda.Stream(device=dev) for _ in range(Lm)]
+        composed = [[torch.cuda.Event() for _ in range(2)] for _ in range(Lm)]
+        copied = [[torch.cuda.Event() for _ in range(2)] for _ in range(Lm)]
+        submitted = [[torch.cuda.Event() for _ in range(2)] for _ in range(Lm)]
+        lane_k = [0] * Lm
+        D = max(1, min(2 * Lm, args.e2e_depth if args.e2e_depth > 0 else Lm))  # frames in flight on the host (at most two per lane)
 
         def e2e_submit(j):
-            l = j % L
+            l = j % Lm
             k = lane_k[l]
             lane_k[l] += 1
             # the lane's frame k - 2 is in host memory already (the host waited for it before submitting this one), so GPU0's
@@ -534,7 +536,7 @@ def run_cuda(args):
             submitted[l][k & 1].record(lane_streams[l])
 
         def e2e_wait(j):
-            l, k = j % L, j // L
+            l, k = j % Lm, j // Lm
             (copied if rank == 0 else submitted)[l][k & 1].synchronize()
 
         def e2e_run(n):
@@ -545,15 +547,15 @@ def run_cuda(args):
             for j in range(max(0, n - (D - 1)), n):
                 e2e_wait(j)
 
-        e2e_run(4 * L)
-        for l in range(L):  # e2e_wait derives a lane's frame number from the run-local index: keep both in step
+        e2e_run(4 * Lm)
+        for l in range(Lm):  # e2e_wait derives a lane's frame number from the run-local index: keep both in step
             assert lane_k[l] % 2 == 0
         ne2e = max(20, min(K, 200))
-        ne2e -= ne2e % (2 * L)
+        ne2e -= ne2e % (2 * Lm)
         base_k = list(lane_k)
 
         def e2e_wait(j):  # noqa: F811 -- the timed run continues the lanes' frame numbers
-            l, k = j % L, base_k[j % L] + j // L
+            l, k = j % Lm, base_k[j % Lm] + j // Lm
             (copied if rank == 0 else submitted)[l][k & 1].synchronize()
 
         barrier()
@@ -566,7 +568,7 @@ def run_cuda(args):
         for cp in comps:
             cp.check()
         if rank == 0:
-            extra["e2e_frames_identical"] = bool(all(torch.equal(host_t[0][0], host_t[l][b]) for l in range(L) for b in range(2)))
+            extra["e2e_frames_identical"] = bool(all(torch.equal(host_t[0][0], host_t[l][b]) for l in range(Lm) for b in range(2)))
 
     # ---- BASELINE cfg 5 (3840x2160, view distance 32): 1 GPU, and at N > 1 the stripe frame with / without the composite ---
     cfg5 = None
@@ -627,7 +629,9 @@ def run_cuda(args):
     d2h = W * H * 4 + 4 * n_lattice + 64  # frame + draw order + control block
     e2e_val, e2e_sync, e2e_note = None, None, None
     if world_size == 1:
-        loop = api.FrameLoop(batch, cfg, view_distance=VD, want_depth=False, ctx=ctx, lanes=L)
+        Le = max(1, min(L, args.e2e_lanes))  # the host loop is PCIe-bound from three lanes on; more only deepen the queue
+        extra["e2e_lanes"] = Le
+        loop = api.FrameLoop(batch, cfg, view_distance=VD, want_depth=False, ctx=ctx, lanes=Le)
         for _ in range(3):
             c_sync, _, s_sync = loop.render(vp, cam.position)
         ref_frame, ref_order = c_sync.copy(), s_sync.copy()
@@ -637,7 +641,7 @@ def run_cuda(args):
         for _ in range(ne2e):
             loop.render(vp, cam.position)
         e2e_sync = ne2e / (time.perf_counter() - t0)
-        D = max(1, min(2 * L, args.e2e_depth if args.e2e_depth > 0 else L))  # frames in flight on the host (measured: deeper queues only add latency)
+        D = max(1, min(2 * Le, args.e2e_depth if args.e2e_depth > 0 else Le))  # frames in flight on the host (measured: deeper queues only add latency)
         extra["e2e_frames_in_flight"] = D
 
         def e2e_run(n):
@@ -646,13 +650,13 @@ def run_cuda(args):
                 pend.append(loop.submit(vp, cam.position))
                 if len(pend) >= D:
                     c_, _, s_ = loop.wait(pend.pop(0))  # that frame is complete in host memory here
-                    ok_ = ok_ and c_[H // 2, W // 2] == ref_frame[H // 2, W // 2]
+                    ok_ = bool(ok_ and c_[H // 2, W // 2] == ref_frame[H // 2, W // 2])
             while pend:
                 c_, _, s_ = loop.wait(pend.pop(0))
                 ok_ = ok_ and bool(np.array_equal(c_, ref_frame) and np.array_equal(s_, ref_order))  # the last D frames in full
-            return ok_
+            return bool(ok_)
 
-        e2e_run(4 * L)
+        e2e_run(4 * Le)
         t0 = time.perf_counter()
         ok = e2e_run(ne2e)
         e2e_val = ne2e / (time.perf_counter() - t0)
@@ -661,9 +665,9 @@ def run_cuda(args):
         extra["e2e_d2h_GBps"] = e2e_val * d2h / 1e9
         if not ok:
             e2e_val = e2e_sync
-        e2e_note = (f"api.FrameLoop(lanes={L}).submit / wait -> vx_render_frame_begin / _end: VP + camera + config in; the frame is rendered into a "
+        e2e_note = (f"api.FrameLoop(lanes={Le}).submit / wait -> vx_render_frame_begin / _end: VP + camera + config in; the frame is rendered into a "
                     "device buffer of its in-flight slot and leaves over the copy engine on a second stream, the ARGB frame, the draw order and "
-                    f"the frame's control block land in page-locked host memory every step; {L} lanes, {D} frames in flight on the host (the "
+                    f"the frame's control block land in page-locked host memory every step; {Le} lanes, {D} frames in flight on the host (the "
                     "oldest is waited for before another is enqueued); the loop is bound by the PCIe transfer of the frame "
                     "(extra.e2e_d2h_GBps); colour only -- the depth plane is frame-internal (the reference presents color_buffer only, "
                     "main.rs:320-322); extra.e2e_synchronous_frames_per_s = one blocking vx_render_frame per step")
@@ -672,7 +676,7 @@ def run_cuda(args):
         extra["e2e_d2h_GBps"] = e2e_val * d2h / 1e9
         e2e_note = ("per step every rank gets VP + camera + config and renders its stripe (vx_render_frame_stripe) straight into GPU0's frame over "
                     "NVLink; GPU0's raster kernel waits for the arrival words, the composed ARGB frame goes to page-locked host memory over the copy "
-                    f"engine (second stream), a buffer is acknowledged two lane-steps later (four buffers per lane); {L} lanes, {min(2 * L, args.e2e_depth if args.e2e_depth > 0 else L)} frames in "
+                    f"engine (second stream), a buffer is acknowledged two lane-steps later (four buffers per lane); {extra.get('e2e_lanes')} lanes, as many frames in "
                     "flight on the host; wall clock between barriers, max over ranks")
 
     # ---- second BASELINE metric: chunks meshed / s (whole-world remesh sweep of the Varied chunks, inputs resident) ----
@@ -1063,7 +1067,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--lanes", type=int, default=3, help="frames in flight on each GPU (api.FrameLanes)")
+    ap.add_argument("--lanes", type=int, default=6, help="frames in flight on each GPU (api.FrameLanes)")
+    ap.add_argument("--e2e-lanes", type=int, default=3, help="lanes of the e2e host loop (at most --lanes)")
     ap.add_argument("--e2e-depth", type=int, default=0, help="frames in flight on the host in the e2e loop (default lanes, at most 2 * lanes)")
     args = ap.parse_args()
     if args.impl == "reference":
