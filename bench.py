@@ -306,7 +306,10 @@ def run_cuda(args):
         dist.broadcast_object_list(holder, src=0)
         stripes = [tuple(x) for x in holder[0]]
         # one compositor (composite buffers + flag words) per lane: a lane is an in-order sequence of frames of its own
-        comps = [multigpu.StripeCompositor(c, W, H, rank, world_size, want_depth=True) for c in lanes.ctxs]
+        # (colour only unless --composite-depth: the depth plane is frame-internal on every GPU -- the reference presents
+        # color_buffer, main.rs:320-322 -- and leaving it out halves what crosses NVLink; the guard below composes both planes)
+        comps = [multigpu.StripeCompositor(c, W, H, rank, world_size, want_depth=bool(args.composite_depth), n_buffers=args.composite_buffers,
+                                           fused_signal=bool(args.fused_signal)) for c in lanes.ctxs]
         for cp in comps:
             cp.set_stripes(stripes)
         comp = comps[0]
@@ -334,6 +337,8 @@ def run_cuda(args):
         for c in lanes.ctxs:
             api.frame_stats(c)  # surfaces an overflow of an async frame, if any
 
+    host_submit = [0.0, 0]  # seconds spent inside the submitting call, calls
+
     def timed_groups(n_frames: int, n_lanes: int):
         """n_frames frames in groups of one frame per lane; every group starts behind an L2 flush.  Device ms, summed over the
         groups: from the end of the flush to the end of the group's last frame."""
@@ -348,7 +353,10 @@ def run_cuda(args):
             for l in range(g):
                 if l:
                     lane_streams[l].wait_event(f_ev)
+                t_h = time.perf_counter()
                 step_device(l, n_lanes)
+                host_submit[0] += time.perf_counter() - t_h
+                host_submit[1] += 1
                 e = torch.cuda.Event(enable_timing=True)
                 e.record(lane_streams[l])
                 ends.append(e)
@@ -377,6 +385,7 @@ def run_cuda(args):
     total_ms = timed_groups(K, L)
     l1 = lanes.launch_count
     launches_per_frame = (l1 - l0) / K
+    extra["host_submit_us_per_frame"] = host_submit[0] / max(1, host_submit[1]) * 1e6  # rank 0's; the device path is asynchronous
     for cp in comps or []:
         cp.check()
     # keep the same load running until the sampler has seen >= 1.5 s of it (the timed frames are ~tens of microseconds)
@@ -399,6 +408,45 @@ def run_cuda(args):
         check_lanes()
     else:
         alone_ms = ms_per_step
+    if comps is not None:
+        # what the hand-off costs: the same stripes, same lanes, rendered into this GPU's own buffers with no flags
+        cfg_local = api.VxFrameConfig.from_buffer_copy(cfg_lanes)
+        cfg_local.stripe_y0, cfg_local.stripe_rows = stripes[rank]
+        saved_comps, comps = comps, None
+        saved_cfg, cfg_lanes = cfg_lanes, cfg_local
+        try:
+            if stripes[rank][1] > 0:
+                for c in lanes.ctxs:
+                    api.render_frame_device(batch, vp, cam.position, cfg_local, VD, c)
+                lanes.synchronize()
+                own_ms = timed_groups(K, L) / K
+            else:
+                own_ms = 0.0
+            # ... and the same with the stripe stored into GPU0's frame (peer stores over NVLink), still without flags
+            peer_ms = 0.0
+            if stripes[rank][1] > 0:
+                off = stripes[rank][0] * W * 4
+                step_saved = step_device
+
+                def step_peer(l: int = 0, in_flight: int = 1):
+                    api.render_frame_into(batch, vp, cam.position, cfg_local, VD, saved_comps[l].color_ptr(0) + off, 0, lanes[l])
+
+                step_device = step_peer
+                try:
+                    for l in range(L):
+                        step_peer(l)
+                    lanes.synchronize()
+                    peer_ms = timed_groups(K, L) / K
+                finally:
+                    step_device = step_saved
+        finally:
+            comps, cfg_lanes = saved_comps, saved_cfg
+        log(f"rank {rank}: stripe into GPU0's frame without flags {peer_ms * 1e3:.1f} us per frame")
+        extra["stripe_ms_peer_stores_no_flags_this_rank"] = peer_ms
+        log(f"rank {rank}: composited frames {total_ms / K * 1e3:.1f} us per frame on this rank, own stripe without hand-off {own_ms * 1e3:.1f} us")
+        barrier()
+        extra["stripe_ms_without_handoff_max_over_ranks"] = max_over_ranks(own_ms)
+        extra["stripe_ms_composited_this_rank"] = total_ms / K
     extra["frame_alone_ms"] = alone_ms
     extra["frames_per_sec_one_frame_in_flight"] = 1000.0 / alone_ms
     frame_no = lane_frame_no[0]
@@ -406,17 +454,19 @@ def run_cuda(args):
     # ---- N > 1 guards (outside the timed region): the composed frame equals this GPU's own full frame, bit for bit;
     #      the assembled batch equals a locally meshed one ------------------------------------------------------------
     if comp is not None:
-        k = frame_no
-        comp.render(batch, vp, cam.position, cfg, VD, k)
-        frame_no += 1
-        lane_frame_no[0] = frame_no
+        lanes.synchronize()
+        barrier()
+        gcomp = multigpu.StripeCompositor(ctx, W, H, rank, world_size, want_depth=True)  # colour + depth, same stripes
+        gcomp.set_stripes(stripes)
+        k = 0
+        gcomp.render(batch, vp, cam.position, cfg, VD, k)
         if rank == 0:
-            comp.complete(k)
+            gcomp.complete(k)
             ctx.synchronize()
-            comp.check()
-            got_c = comp.frame_tensor(k, dev).cpu().numpy().view(np.uint32)
-            got_d = comp.depth_tensor(k, dev).cpu().numpy().view(np.uint32)
-            comp.release(k)
+            gcomp.check()
+            got_c = gcomp.frame_tensor(k, dev).cpu().numpy().view(np.uint32)
+            got_d = gcomp.depth_tensor(k, dev).cpu().numpy().view(np.uint32)
+            gcomp.release(k)
             local = mesh_full_locally()
             api.render_frame_device(local, vp, cam.position, cfg, VD, ctx)
             dc, dd, rows_, width_ = api.framebuffer_device(ctx)
@@ -433,6 +483,7 @@ def run_cuda(args):
             local.release()
         ctx.synchronize()
         barrier()
+        gcomp.close()
 
     # ---- chunk-sharded remesh sweep (BASELINE cfg 4): rank r re-meshes the lattice chunks k with k % N == r, the packed
     #      shards are all-gathered (NCCL) and every rank rebuilds the full batch -- the exchange is inside the timed region
@@ -1069,6 +1120,9 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--lanes", type=int, default=6, help="frames in flight on each GPU (api.FrameLanes)")
     ap.add_argument("--e2e-lanes", type=int, default=3, help="lanes of the e2e host loop (at most --lanes)")
+    ap.add_argument("--fused-signal", type=int, default=0, help="N > 1: 1 = every rank's raster kernel publishes its own arrival word")
+    ap.add_argument("--composite-buffers", type=int, default=2, help="N > 1: composed-frame buffers per lane")
+    ap.add_argument("--composite-depth", type=int, default=0, help="N > 1: 1 = the timed stripes also store their depth plane into GPU0's frame")
     ap.add_argument("--e2e-depth", type=int, default=0, help="frames in flight on the host in the e2e loop (default lanes, at most 2 * lanes)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -693,9 +693,15 @@ def render_frame_device(batch: MeshBatch, view_proj, camera_position, cfg: VxFra
                         ctx: Optional[Context] = None):
     """Device-resident frame: filter A on the device over the batch's chunks, nothing copied back."""
     ctx = ctx or batch.ctx
-    vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
-    cam = np.ascontiguousarray(camera_position, dtype=np.float32).reshape(3)
-    ctx.check(ctx.lib.vx_render_frame_device(ctx.handle, batch.handle, None, -1, _p(vp), _p(cam), int(view_distance), C.byref(cfg)))
+    st = getattr(ctx, "_rfd_state", None)
+    if st is None:  # the argument buffers are kept per context: the host side of a frame has to stay at a few microseconds
+        vp_a, cam_a = np.zeros(16, dtype=np.float32), np.zeros(3, dtype=np.float32)
+        st = ctx._rfd_state = (vp_a, cam_a, _p(vp_a), _p(cam_a), ctx.lib.vx_render_frame_device)
+    st[0][:] = np.asarray(view_proj, dtype=np.float32).reshape(16)
+    st[1][:] = camera_position
+    rc = st[4](ctx.handle, batch.handle, None, -1, st[2], st[3], int(view_distance), C.byref(cfg))
+    if rc != 0:
+        ctx.check(rc)
 
 
 def render_frame_into(batch: MeshBatch, view_proj, camera_position, cfg: VxFrameConfig, view_distance: int, d_color: int,

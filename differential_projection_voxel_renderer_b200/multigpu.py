@@ -47,10 +47,15 @@ class StripeCompositor:
     """
 
     def __init__(self, ctx: api.Context, width: int, height: int, rank: int, world: int, group=None, dst: int = 0,
-                 n_buffers: int = 2, want_depth: bool = False, timeout_us: int = 2_000_000):
+                 n_buffers: int = 2, want_depth: bool = False, timeout_us: int = 2_000_000, fused_signal: bool = False):
         import torch.distributed as dist
         self.ctx, self.W, self.H, self.rank, self.world, self.dst, self.group = ctx, int(width), int(height), rank, world, dst, group
         self.n_buffers, self.want_depth, self.timeout_us = int(n_buffers), bool(want_depth), int(timeout_us)
+        # Who publishes a rank's arrival word.  Fused into the raster kernel, every CTA has to fence its peer stores at system
+        # scope before it counts itself out -- 592 CTAs each holding their SM slot for an NVLink round trip; with several
+        # frames in flight that costs more (27 -> 34 us per frame at N = 2) than one 32-thread kernel behind the raster kernel,
+        # whose completion flushes the stores anyway.  The composing GPU's own stripe stays fused (its stores are local).
+        self.fused_signal = bool(fused_signal)
         lib, h = ctx.lib, ctx.handle
         self.frame_bytes = self.W * self.H * 4
         planes = 2 if want_depth else 1
@@ -93,6 +98,7 @@ class StripeCompositor:
             self.arrive = open_(everyone[dst]["arrive"]).value
             self.acks = None
         self.stripes: List[Tuple[int, int]] = []
+        self._call_state = None
         self.set_stripes(None)
         dist.barrier(group=group)
 
@@ -133,25 +139,49 @@ class StripeCompositor:
         wait_needed = frame_no >= self.n_buffers  # the buffer is free once dst has consumed frame_no - n_buffers
         if rows > 0:
             # hand-off fused into the raster kernel: it waits for the acknowledgement before its first store into the frame
-            # and its last CTA publishes the arrival word -- three launches per stripe, none of them a hand-off kernel
-            c = api.VxFrameConfig.from_buffer_copy(cfg)
+            # and its last CTA publishes the arrival word -- three launches per stripe, none of them a hand-off kernel.
+            # (The ctypes objects are kept between calls: at tens of thousands of frames per second the host side of a frame
+            # has to stay in the single-digit microseconds.)
+            st = self._call_state
+            if st is None:
+                st = self._call_state = {"cfg": api.VxFrameConfig(), "sync": VxStripeSync(), "vp": np.zeros(16, np.float32), "cam": np.zeros(3, np.float32),
+                                         "rel": (C.c_void_p * self.world)(*self.acks) if self.acks is not None else None}
+                st["cfg_ref"], st["sync_ref"] = C.byref(st["cfg"]), C.byref(st["sync"])
+                st["vp_p"], st["cam_p"] = st["vp"].ctypes.data_as(C.c_void_p), st["cam"].ctypes.data_as(C.c_void_p)
+                st["rel_p"] = C.cast(st["rel"], C.c_void_p) if st["rel"] is not None else None
+                st["fn"] = lib.vx_render_frame_stripe
+            c, sync = st["cfg"], st["sync"]
+            C.memmove(st["cfg_ref"], C.byref(cfg), C.sizeof(api.VxFrameConfig))
             c.stripe_y0, c.stripe_rows = y0, rows
             off = y0 * self.W * 4
-            sync = VxStripeSync(self.ack_local.value if wait_needed else None, (frame_no - self.n_buffers + 1) & 0xFFFFFFFF if wait_needed else 0,
-                                arrive, (frame_no + 1) & 0xFFFFFFFF, self.timeout_us)
+            sync.d_wait_flag = self.ack_local.value if wait_needed else None
+            sync.wait_value = (frame_no - self.n_buffers + 1) & 0xFFFFFFFF if wait_needed else 0
+            publish_after = not self.fused_signal and self.rank != self.dst
+            sync.d_signal_flag = None if publish_after else arrive
+            sync.signal_value = (frame_no + 1) & 0xFFFFFFFF
+            sync.timeout_us = self.timeout_us
             fused = compose_release is not None and self.rank == self.dst
             if fused:
-                self._rel_table = (C.c_void_p * self.world)(*self.acks)
                 sync.n_arrive, sync.arrive_stride_words, sync.d_arrive_flags = self.world, FLAG_STRIDE_WORDS, self.arrive
                 sync.arrive_value = (frame_no + 1) & 0xFFFFFFFF
                 sync.release_value = (compose_release + 1) & 0xFFFFFFFF if compose_release >= 0 else 0
                 sync.n_release = self.world if compose_release >= 0 else 0
-                sync.release_flags = C.cast(self._rel_table, C.c_void_p)
-            vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
-            cam = np.ascontiguousarray(camera_position, dtype=np.float32).reshape(3)
-            ctx.check(lib.vx_render_frame_stripe(h, batch.handle, None, -1, api._p(vp), api._p(cam), int(view_distance), C.byref(c),
-                                                 C.c_void_p(self.color_ptr(frame_no) + off),
-                                                 C.c_void_p(self.depth_ptr(frame_no) + off) if self.want_depth else None, C.byref(sync)))
+                sync.release_flags = st["rel_p"]
+            else:
+                sync.n_arrive = 0
+                sync.n_release = 0
+            st["vp"][:] = np.asarray(view_proj, dtype=np.float32).reshape(16)
+            st["cam"][:] = camera_position
+            rc = st["fn"](h, batch.handle, None, -1, st["vp_p"], st["cam_p"], int(view_distance), st["cfg_ref"],
+                          self.color_ptr(frame_no) + off, (self.depth_ptr(frame_no) + off) if self.want_depth else None, st["sync_ref"])
+            if rc != 0:
+                ctx.check(rc)
+            if publish_after:
+                if "flag1" not in st:
+                    st["flag1"] = (C.c_void_p * 1)(arrive)
+                rc = lib.vx_signal_flags(h, st["flag1"], 1, (frame_no + 1) & 0xFFFFFFFF)
+                if rc != 0:
+                    ctx.check(rc)
             return fused
         # a rank without rows only reports in
         if wait_needed:
