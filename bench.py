@@ -339,25 +339,35 @@ def run_cuda(args):
 
     host_submit = [0.0, 0]  # seconds spent inside the submitting call, calls
 
+    ev_pool = []  # timing events are created ahead of the timed loops: creating one costs the host ~2 us
+
+    def take_event():
+        return ev_pool.pop() if ev_pool else torch.cuda.Event(enable_timing=True)
+
     def timed_groups(n_frames: int, n_lanes: int):
         """n_frames frames in groups of one frame per lane; every group starts behind an L2 flush.  Device ms, summed over the
         groups: from the end of the flush to the end of the group's last frame."""
+        n_groups = (n_frames + n_lanes - 1) // n_lanes
+        while len(ev_pool) < n_groups * (n_lanes + 1):
+            ev_pool.append(torch.cuda.Event(enable_timing=True))
         groups = []
         done = 0
+        perf = time.perf_counter
         while done < n_frames:
             g = min(n_lanes, n_frames - done)
             flush_l2()
-            f_ev = torch.cuda.Event(enable_timing=True)
+            f_ev = take_event()
             f_ev.record(lane_streams[0])
             ends = []
+            for l in range(1, g):
+                lane_streams[l].wait_event(f_ev)
+            t_h = perf()
             for l in range(g):
-                if l:
-                    lane_streams[l].wait_event(f_ev)
-                t_h = time.perf_counter()
                 step_device(l, n_lanes)
-                host_submit[0] += time.perf_counter() - t_h
-                host_submit[1] += 1
-                e = torch.cuda.Event(enable_timing=True)
+            host_submit[0] += perf() - t_h
+            host_submit[1] += g
+            for l in range(g):
+                e = take_event()
                 e.record(lane_streams[l])
                 ends.append(e)
             for l in range(1, g):
@@ -365,7 +375,11 @@ def run_cuda(args):
             groups.append((f_ev, ends))
             done += g
         torch.cuda.synchronize()
-        return sum(max(f_ev.elapsed_time(e) for e in ends) for f_ev, ends in groups)
+        total = sum(max(f_ev.elapsed_time(e) for e in ends) for f_ev, ends in groups)
+        for f_ev, ends in groups:
+            ev_pool.append(f_ev)
+            ev_pool.extend(ends)
+        return total
 
     # ---- warm-up ---------------------------------------------------------------------------------------------------
     Wm = max(3, args.warmup)
@@ -386,6 +400,9 @@ def run_cuda(args):
     l1 = lanes.launch_count
     launches_per_frame = (l1 - l0) / K
     extra["host_submit_us_per_frame"] = host_submit[0] / max(1, host_submit[1]) * 1e6  # rank 0's; the device path is asynchronous
+    if world_size > 1:
+        log(f"rank {rank}: host submit {host_submit[0] / max(1, host_submit[1]) * 1e6:.1f} us per frame")
+        extra["host_submit_us_per_frame_max_over_ranks"] = max_over_ranks(host_submit[0] / max(1, host_submit[1]) * 1e6)
     for cp in comps or []:
         cp.check()
     # keep the same load running until the sampler has seen >= 1.5 s of it (the timed frames are ~tens of microseconds)

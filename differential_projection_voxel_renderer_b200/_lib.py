@@ -68,7 +68,7 @@ class VxMeshBatchDevice(C.Structure):
 class VxStripeSync(C.Structure):
     _fields_ = [("d_wait_flag", C.c_void_p), ("wait_value", C.c_uint32), ("d_signal_flag", C.c_void_p), ("signal_value", C.c_uint32),
                 ("timeout_us", C.c_int32), ("n_arrive", C.c_int32), ("arrive_stride_words", C.c_int32), ("d_arrive_flags", C.c_void_p),
-                ("arrive_value", C.c_uint32), ("release_value", C.c_uint32), ("n_release", C.c_int32), ("reserved", C.c_int32),
+                ("arrive_value", C.c_uint32), ("release_value", C.c_uint32), ("n_release", C.c_int32), ("signal_after", C.c_int32),
                 ("release_flags", C.c_void_p)]
 
 

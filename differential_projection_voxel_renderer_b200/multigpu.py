@@ -156,8 +156,8 @@ class StripeCompositor:
             off = y0 * self.W * 4
             sync.d_wait_flag = self.ack_local.value if wait_needed else None
             sync.wait_value = (frame_no - self.n_buffers + 1) & 0xFFFFFFFF if wait_needed else 0
-            publish_after = not self.fused_signal and self.rank != self.dst
-            sync.d_signal_flag = None if publish_after else arrive
+            sync.signal_after = 1 if (not self.fused_signal and self.rank != self.dst) else 0
+            sync.d_signal_flag = arrive
             sync.signal_value = (frame_no + 1) & 0xFFFFFFFF
             sync.timeout_us = self.timeout_us
             fused = compose_release is not None and self.rank == self.dst
@@ -170,18 +170,16 @@ class StripeCompositor:
             else:
                 sync.n_arrive = 0
                 sync.n_release = 0
-            st["vp"][:] = np.asarray(view_proj, dtype=np.float32).reshape(16)
-            st["cam"][:] = camera_position
+            if view_proj is not st.get("vp_src") or camera_position is not st.get("cam_src"):
+                st["vp"][:] = np.asarray(view_proj, dtype=np.float32).reshape(16)
+                st["cam"][:] = camera_position
+                # immutable inputs (tuples) may be recognised by identity next time; arrays may be changed in place by the caller
+                st["vp_src"] = view_proj if isinstance(view_proj, tuple) else None
+                st["cam_src"] = camera_position if isinstance(camera_position, tuple) else None
             rc = st["fn"](h, batch.handle, None, -1, st["vp_p"], st["cam_p"], int(view_distance), st["cfg_ref"],
                           self.color_ptr(frame_no) + off, (self.depth_ptr(frame_no) + off) if self.want_depth else None, st["sync_ref"])
             if rc != 0:
                 ctx.check(rc)
-            if publish_after:
-                if "flag1" not in st:
-                    st["flag1"] = (C.c_void_p * 1)(arrive)
-                rc = lib.vx_signal_flags(h, st["flag1"], 1, (frame_no + 1) & 0xFFFFFFFF)
-                if rc != 0:
-                    ctx.check(rc)
             return fused
         # a rank without rows only reports in
         if wait_needed:

@@ -5,7 +5,7 @@ set -x
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
 timeout 900 python bench.py --steps 200 --warmup 10 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; echo bench rc=$?
 tail -3 gpurun_out/bench_${TAG}.err
-for l in 1 2 4 6; do
+for l in 1 3 8; do
 timeout 900 python bench.py --steps 200 --warmup 10 --lanes $l > gpurun_out/bench_${TAG}_lanes$l.json 2> gpurun_out/bench_${TAG}_lanes$l.err; echo bench lanes $l rc=$?
 done
 timeout 600 python bench.py --impl reference --steps 20 --warmup 2 > gpurun_out/bench_ref_${TAG}.json 2> gpurun_out/bench_ref_${TAG}.err; echo ref rc=$?
