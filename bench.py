@@ -317,14 +317,17 @@ def run_cuda(args):
     cfg_stripe_lanes = api.VxFrameConfig.from_buffer_copy(cfg)
     cfg_stripe_lanes.frames_in_flight = L
 
+    # the same camera every step: passed as tuples, which the host API recognises by identity (no per-call conversion)
+    vp_t, cam_t = tuple(float(x) for x in np.asarray(vp, dtype=np.float32).reshape(16)), tuple(float(x) for x in cam.position)
+
     def step_device(l: int = 0, in_flight: int = 1):
         if comps is None:
-            api.render_frame_device(batch, vp, cam.position, cfg_lanes if in_flight > 1 else cfg_async, VD, lanes[l])
+            api.render_frame_device(batch, vp_t, cam_t, cfg_lanes if in_flight > 1 else cfg_async, VD, lanes[l])
         else:
             # hand-off fused into the raster kernels: every rank's last CTA publishes its stripe, GPU0's last CTA waits for all
             # of them and hands the buffer back -- three launches per rank and frame, none of them a hand-off kernel
             k = lane_frame_no[l]
-            fused = comps[l].render(batch, vp, cam.position, cfg_stripe_lanes if in_flight > 1 else cfg, VD, k,
+            fused = comps[l].render(batch, vp_t, cam_t, cfg_stripe_lanes if in_flight > 1 else cfg, VD, k,
                                     compose_release=k if rank == 0 else None)
             if rank == 0 and not fused:
                 comps[l].complete_and_release(k)
@@ -1135,7 +1138,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--lanes", type=int, default=6, help="frames in flight on each GPU (api.FrameLanes)")
+    ap.add_argument("--lanes", type=int, default=8, help="frames in flight on each GPU (api.FrameLanes)")
     ap.add_argument("--e2e-lanes", type=int, default=3, help="lanes of the e2e host loop (at most --lanes)")
     ap.add_argument("--fused-signal", type=int, default=0, help="N > 1: 1 = every rank's raster kernel publishes its own arrival word")
     ap.add_argument("--composite-buffers", type=int, default=2, help="N > 1: composed-frame buffers per lane")

@@ -696,9 +696,13 @@ def render_frame_device(batch: MeshBatch, view_proj, camera_position, cfg: VxFra
     st = getattr(ctx, "_rfd_state", None)
     if st is None:  # the argument buffers are kept per context: the host side of a frame has to stay at a few microseconds
         vp_a, cam_a = np.zeros(16, dtype=np.float32), np.zeros(3, dtype=np.float32)
-        st = ctx._rfd_state = (vp_a, cam_a, _p(vp_a), _p(cam_a), ctx.lib.vx_render_frame_device)
-    st[0][:] = np.asarray(view_proj, dtype=np.float32).reshape(16)
-    st[1][:] = camera_position
+        st = ctx._rfd_state = [vp_a, cam_a, _p(vp_a), _p(cam_a), ctx.lib.vx_render_frame_device, None, None]
+    if view_proj is not st[5] or camera_position is not st[6]:
+        st[0][:] = np.asarray(view_proj, dtype=np.float32).reshape(16)
+        st[1][:] = camera_position
+        # immutable inputs (tuples) are recognised by identity next time; arrays may be changed in place by the caller
+        st[5] = view_proj if isinstance(view_proj, tuple) else None
+        st[6] = camera_position if isinstance(camera_position, tuple) else None
     rc = st[4](ctx.handle, batch.handle, None, -1, st[2], st[3], int(view_distance), C.byref(cfg))
     if rc != 0:
         ctx.check(rc)
