@@ -4,6 +4,8 @@ Criteria (BASELINE.json north_star): visible-chunk sets bit-exact; projected ver
 framebuffer depth within 1e-6; colour mismatches on at most 0.1 % of pixels.  In the default (exact-arithmetic)
 mode the CUDA path is held to a stricter bar: draw order, depth and colour bit-identical to the oracle.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -302,6 +304,22 @@ def test_full_size_frame_1280x720_vd12(ctx, ob):
     # idempotence: a second frame is identical
     color2, depth2, _ = api.render_frame(batch, vp, cam.position, cfg, mesh_ids=None, view_distance=12, ctx=ctx)
     assert np.array_equal(color2, color) and np.array_equal(depth2.view(np.uint32), depth.view(np.uint32))
+    # the frames_in_flight hint only changes how the raster work is CUT (work items sized from the previous frame's task
+    # total: 256 tasks per item alone, ~1500 at 8, one item per tile at 64), never a pixel: several frames each, so that
+    # the plan of the compared frame was made with the hint
+    items_seen = []
+    for fif in (0, 3, 8, 64):
+        cfg_h = api.VxFrameConfig.from_buffer_copy(cfg)
+        cfg_h.frames_in_flight = fif
+        for _ in range(3):
+            color_h, depth_h, surv_h = api.render_frame(batch, vp, cam.position, cfg_h, mesh_ids=None, view_distance=12, ctx=ctx)
+        assert np.array_equal(surv_h, osurv), f"frames_in_flight {fif}"
+        assert np.array_equal(color_h, oc) and np.array_equal(depth_h.view(np.uint32), od.view(np.uint32)), f"frames_in_flight {fif}"
+        cnt = (C.c_uint32 * 32)()
+        ctx.check(ctx.lib.vx_frame_counters(ctx.handle, cnt))
+        items_seen.append(int(cnt[9]))
+        assert cnt[14] > 0  # tasks binned: what the next frame's plan divides
+    assert items_seen[0] > items_seen[2] > items_seen[3], items_seen  # coarser items with more frames in flight
     cfg.differential_projection = 1
     color3, depth3, _ = api.render_frame(batch, vp, cam.position, cfg, mesh_ids=None, view_distance=12, ctx=ctx)
     assert float((color3 != oc).mean()) <= COLOR_MISMATCH_MAX

@@ -22,6 +22,7 @@ print("quads", batch.info().total_quads)
 vb = api.BinaryGreedyMesher.mesh_batch(v, p, nb, None, ctx)  # and one re-mesh of the Varied chunks for the mesher's line in the launch list
 vb.release()
 cfg = api.default_frame_config(1280, 720)
+cfg.frames_in_flight = int(os.environ.get("VX_FRAMES_IN_FLIGHT", "0"))  # > 1: the coarser work items of a frame that shares the GPU
 for _ in range(frames):
     api.render_frame_device(batch, cam.view_projection(), cam.position, cfg, 12, ctx)
 ctx.synchronize()
