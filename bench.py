@@ -301,8 +301,9 @@ def run_cuda(args):
     stripes = [(0, H)]
     lane_frame_no = [0] * L
     if world_size > 1:
-        band = api.frame_bin_counts(ctx).sum(axis=1).astype(np.float64)  # triangles binned per 8-row band of the full frame
-        holder = [sharding.balanced_stripes(band, H, world_size, band=8, row_cost=float(band.sum()) / (4.0 * H))] if rank == 0 else [None]
+        # cost of every 8-row band of the full frame: bin entries + the tasks they expand to (sharding.stripe_band_cost)
+        band = sharding.stripe_band_cost(api.frame_bin_counts(ctx), api.frame_bin_tasks(ctx))
+        holder = [sharding.balanced_stripes(band, H, world_size, band=8, row_cost=float(band.sum()) / (20.0 * H))] if rank == 0 else [None]
         dist.broadcast_object_list(holder, src=0)
         stripes = [tuple(x) for x in holder[0]]
         # one compositor (composite buffers + flag words) per lane: a lane is an in-order sequence of frames of its own

@@ -152,6 +152,7 @@ PROTOTYPES = {
     "vx_frame_trace": (C.c_int, [_P, _P, _I, C.POINTER(_I)]),
     "vx_frame_setup_trace": (C.c_int, [_P, _P, _I, C.POINTER(_I)]),
     "vx_frame_bin_counts": (C.c_int, [_P, _P, _I, C.POINTER(_I), C.POINTER(_I)]),
+    "vx_frame_bin_tasks": (C.c_int, [_P, _P, _I, C.POINTER(_I), C.POINTER(_I)]),
     "vx_render_mesh": (C.c_int, [_P, _P, _I, _P, C.POINTER(VxFrameConfig), _P, _P, _P]),
     "vx_face_packets": (C.c_int, [_P, _P, _I, _P, _I, _P]),
     "vx_face_basis": (C.c_int, [_P, _P, _P, _P, _I, _P, _P]),

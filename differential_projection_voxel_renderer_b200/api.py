@@ -739,6 +739,15 @@ def frame_bin_counts(ctx: Context) -> np.ndarray:
     return out[:ntx.value * nty.value].reshape(nty.value, ntx.value).copy()
 
 
+def frame_bin_tasks(ctx: Context) -> np.ndarray:
+    """(nty, ntx) (row, 16-pixel column block) tasks per 128x8 tile in the last frame: with frame_bin_counts the cost model
+    of the work-balanced stripe split (sharding.stripe_band_cost)."""
+    out = np.zeros(1 << 16, dtype=np.uint32)
+    ntx, nty = C.c_int32(), C.c_int32()
+    ctx.check(ctx.lib.vx_frame_bin_tasks(ctx.handle, _p(out), out.size, C.byref(ntx), C.byref(nty)))
+    return out[:ntx.value * nty.value].reshape(nty.value, ntx.value).copy()
+
+
 def framebuffer_device(ctx: Context):
     dc, dd, rows, width = C.c_void_p(), C.c_void_p(), C.c_int32(), C.c_int32()
     ctx.check(ctx.lib.vx_framebuffer_device(ctx.handle, C.byref(dc), C.byref(dd), C.byref(rows), C.byref(width)))

@@ -66,6 +66,18 @@ def balanced_stripes(band_cost, height: int, world: int, band: int = 8, row_cost
     return out
 
 
+def stripe_band_cost(bin_entries, bin_tasks) -> np.ndarray:
+    """Per 8-row band: what the band adds to a stripe's frame time, in units of one bin entry.  bin_entries / bin_tasks
+    are the (tile rows, tile columns) arrays of vx_frame_bin_counts / vx_frame_bin_tasks of a calibration frame.  Fitted
+    on a B200 over 16 stripes of the 1280x720 vd12 frame with eight frames in flight (tools/stripe_probe.py):
+    t_stripe = 16.9 us + 1.65e-4 us x entries + 3.4e-5 us x tasks (rms error 1.4 us) -- an entry (a triangle's record load,
+    its span setup) weighs about as much as five of the (row, 16-pixel block) tasks it expands to; the constant (cull
+    kernel, every mesh's setup unit, clear) is the same for every stripe and does not enter the split."""
+    e = np.asarray(bin_entries, dtype=np.float64)
+    t = np.asarray(bin_tasks, dtype=np.float64)
+    return e.sum(axis=1) + t.sum(axis=1) / 4.9
+
+
 def merge_mesh_shards(shards: Sequence[Dict[str, np.ndarray]], n_chunks: int, world: Optional[int] = None) -> Dict[str, np.ndarray]:
     """Put per-rank mesh shards (dicts as MeshBatch.download(): quads (Q,3), quad_count, slice_offsets (n,6,33),
     face_aabb (n,6,6), has_mesh; shard r holds the chunks chunk_shard(n_chunks, r, world) in that order) back into

@@ -430,6 +430,9 @@ VX_API int vx_frame_trace(VxContext *ctx, uint64_t *out, int32_t cap_items, int3
 VX_API int vx_frame_setup_trace(VxContext *ctx, uint64_t *out, int32_t cap_ctas, int32_t *n_ctas);
 /* Diagnostics: triangles binned per 128x8 tile in the last frame (row-major tile grid, ntx x nty). */
 VX_API int vx_frame_bin_counts(VxContext *ctx, uint32_t *counts_out, int32_t cap, int32_t *ntx, int32_t *nty);
+/* Same layout: the (row, 16-pixel column block) tasks the tile's entries expand to -- with the entry counts the cost model of
+ * the work-balanced stripe split (a stripe costs ~ entries + tasks / 5 on top of what every stripe costs). */
+VX_API int vx_frame_bin_tasks(VxContext *ctx, uint32_t *tasks_out, int32_t cap, int32_t *ntx, int32_t *nty);
 
 /* render_frame_macrotile (macrotile_renderer.rs:51-170; MacroTileBins::add_mesh macrotile.rs:179-224, MacroTile as
  * PixelTarget :300-343): clear, project_mesh_aabb per mesh of the caller's list (:175-250, the arithmetic of filter B),

@@ -66,7 +66,8 @@ def _worker(rank, world, port, out_dir, n_dev):
         # full frame once on every rank: scratch sizing + the per-band work the balanced split is derived from
         _, _, order = api.render_frame(batch, vp, cam.position, cfg, mesh_ids=None, view_distance=vd, ctx=ctx)
         assert np.array_equal(order, osurv)
-        band = api.frame_bin_counts(ctx).sum(axis=1).astype(np.float64)
+        band = sharding.stripe_band_cost(api.frame_bin_counts(ctx), api.frame_bin_tasks(ctx))
+        assert band.shape == ((h + 7) // 8,) and band.sum() > 0
         comp = multigpu.StripeCompositor(ctx, w, h, rank, world, want_depth=True, timeout_us=20_000_000)
         for layout in (None, sharding.balanced_stripes(band, h, world), [(0, 8), (8, h - 8)], [(0, h), (h, 0)]):
             comp.set_stripes(layout)
