@@ -102,7 +102,7 @@ class FrameLanes:
     existing context), dealt out round-robin.  One frame is a chain of three dependent, latency-bound kernels that leaves
     most of the GPU's issue slots idle; frames of different lanes are independent (each lane plans its raster work from
     its own previous frame), so their kernels run side by side and the device's frame throughput rises by about a half
-    (1280x720 view distance 12 on a B200: 73 us per frame alone, 48 us with three lanes).  A lane is just a VxContext:
+    (1280x720 view distance 12 on a B200: 74 us per frame alone, 43 us with three lanes, 34 us with eight).  A lane is just a VxContext:
     the C-ABI side of this is vx_context_create called `lanes` times."""
 
     def __init__(self, device: int = 0, lanes: int = 3, first: Optional[Context] = None):
