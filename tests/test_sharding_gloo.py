@@ -153,3 +153,25 @@ def test_balanced_stripes_cover_the_frame_and_even_out_the_work():
     assert sum(r for _, r in st) == 13 and [y for y, _ in st] == sorted(y for y, _ in st)
     with pytest.raises(ValueError):
         sharding.balanced_stripes(np.ones(3), 32, 2)
+
+
+def test_stripe_band_cost_weighs_entries_and_tasks():
+    """sharding.stripe_band_cost: per tile row, bin entries + tasks / 4.9 (the fit of measured stripe costs); a band of few
+    large triangles (few entries, many tasks) weighs as much as a band of many small ones, which an entries-only split
+    would leave to one rank."""
+    from differential_projection_voxel_renderer_b200 import sharding
+    entries = np.zeros((90, 10), dtype=np.uint32)
+    tasks = np.zeros((90, 10), dtype=np.uint32)
+    entries[42:54] = 350     # horizon: many small triangles, one or two tasks each
+    tasks[42:54] = 600
+    entries[54:] = 12        # near terrain: few triangles, hundreds of (row, column block) tasks each
+    tasks[54:] = 2400
+    cost = sharding.stripe_band_cost(entries, tasks)
+    assert cost.shape == (90,) and cost[:42].sum() == 0
+    assert np.isclose(cost[42], 10 * (350 + 600 / 4.9)) and np.isclose(cost[60], 10 * (12 + 2400 / 4.9))
+    by_entries = sharding.balanced_stripes(entries.sum(axis=1).astype(np.float64), 720, 2)
+    by_cost = sharding.balanced_stripes(cost, 720, 2)
+    # the entries-only split cuts inside the horizon band; the cost split moves the cut down, the bottom stripe gets less
+    assert by_cost[0][1] > by_entries[0][1]
+    halves = [cost[y0 // 8:(y0 + r) // 8].sum() for y0, r in by_cost]
+    assert max(halves) / sum(halves) < 0.56
