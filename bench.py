@@ -539,8 +539,10 @@ def run_cuda(args):
         sharded = {"lattice_chunks": n_lattice, "varied_chunks": n_varied, "ms_with_exchange_max_over_ranks": shard_ms,
                    "varied_chunks_meshed_per_sec_with_exchange": n_varied / (shard_ms * 1e-3),
                    "ms_mesh_only_max_over_ranks": noex_ms, "exchanged_bytes_per_rank": int(exchange.exchanged_bytes),
-                   "how": f"chunk id modulo {world_size}; per sweep: mesh kernel on the shard, totals all-gather (ragged sizes), pack, ONE NCCL "
-                          "all_gather_into_tensor of the shard blocks, vx_mesh_batch_assemble_shards on every rank"}
+                   "shards_fitted_their_blocks": bool(exchange.check()),
+                   "how": f"chunk id modulo {world_size}; per sweep, no host round trip: mesh kernel on the shard, vx_mesh_shard_pack_async (the block "
+                          "carries the shard's quad total), ONE NCCL all_gather_into_tensor of the shard blocks, vx_mesh_batch_assemble_shards_async "
+                          "on every rank (the first sweep sized the blocks through the synchronous pair)"}
 
     # ---- alternate-frame rendering (every rank renders whole frames, no exchange): context only, not the headline ---------
     afr_fps = None
@@ -1037,6 +1039,33 @@ def bench_cfg5(torch, api, multigpu, sharding, ctx, stream, dev, rank, world_siz
                     "note": "frame_ms = work-balanced stripes, every raster kernel stores its rows (colour + depth) into GPU0's frame over NVLink, "
                             "GPU0 waits for the arrival flags; max over ranks"})
     api.frame_stats(ctx)
+    # ---- BASELINE cfg 4 at this world's size: whole-world remesh sweep of the 5,877 Varied chunks (8 resident waves on one
+    #      GPU), on one GPU and -- at N > 1 -- sharded by chunk id with the device exchange inside the timed region ----------
+    try:
+        n5 = int(p5.shape[0])
+        d_v5 = torch.from_numpy(v5).to(dev)
+        d_nb5 = torch.from_numpy(nb5).to(dev)
+        d_p5 = torch.from_numpy(p5).to(dev)
+
+        def remesh5():
+            ctx.check(ctx.lib.vx_remesh_chunks_device(ctx.handle, C.c_void_p(d_v5.data_ptr()), C.c_void_p(d_nb5.data_ptr()), None, batch5.handle))
+
+        ms_r1 = timed(remesh5, n=10)
+        out["remesh_world_chunks"] = n5
+        out["remesh_world_ms_one_gpu"] = ms_r1
+        out["chunks_meshed_per_sec_one_gpu"] = n5 / (ms_r1 * 1e-3)
+        if world_size > 1:
+            ex5 = multigpu.MeshShardExchange(ctx, n5, rank, world_size, dev)
+            ex5.sweep(d_v5.data_ptr(), d_p5.data_ptr(), d_nb5.data_ptr(), 0)
+            ms_rs = timed(lambda: ex5.sweep(d_v5.data_ptr(), d_p5.data_ptr(), d_nb5.data_ptr(), 0), n=10)
+            out["remesh_world_ms_sharded_with_exchange"] = ms_rs
+            out["chunks_meshed_per_sec_sharded_with_exchange"] = n5 / (ms_rs * 1e-3)
+            same5 = int(ex5.full.info().total_quads) == int(batch5.info().total_quads)
+            out["sharded_world_same_quad_total"] = bool(same5)
+            ex5.close()
+        del d_v5, d_nb5, d_p5
+    except Exception as e:  # noqa: BLE001 -- context numbers only
+        out["remesh_error"] = repr(e)
     batch5.release()
     del v5, world5
     return out

@@ -108,7 +108,9 @@ PROTOTYPES = {
     "vx_wait_status": (C.c_int, [_P, C.POINTER(_I)]),
     "vx_shard_layout": (C.c_int, [_I, C.c_int64, C.POINTER(VxShardLayout)]),
     "vx_mesh_shard_pack": (C.c_int, [_P, _P, C.POINTER(VxShardLayout), _P]),
+    "vx_mesh_shard_pack_async": (C.c_int, [_P, _P, C.POINTER(VxShardLayout), _P]),
     "vx_mesh_batch_assemble_shards": (C.c_int, [_P, _I, _I, _P, C.POINTER(VxShardLayout), _P, _P, C.POINTER(_P)]),
+    "vx_mesh_batch_assemble_shards_async": (C.c_int, [_P, _I, _I, _P, C.POINTER(VxShardLayout), _P, C.POINTER(_P)]),
     "vx_generate_terrain": (C.c_int, [_P, _P, _I, C.POINTER(VxTerrainParams), _P, _P]),
     "vx_mesh_chunks": (C.c_int, [_P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
     "vx_mesh_batch_update": (C.c_int, [_P, _P, _P, _I, _P, _P, C.POINTER(_I)]),

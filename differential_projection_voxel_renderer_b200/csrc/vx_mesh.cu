@@ -559,9 +559,46 @@ struct ShardOffsets {
 };
 
 // one CTA per chunk of the assembled batch: copy its row from the gathered shard blocks (vx_mesh_batch_assemble_shards)
+// first quad of every rank's stream in the assembled stream, from the totals the blocks carry (no host round trip): one thread
+__global__ void shard_offsets_kernel(int world, const uint8_t *__restrict__ blocks, VxShardLayout L, uint32_t *off /* [64] offsets, [64] totals */,
+                                     unsigned long long *cursor, unsigned long long cap_quads) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    unsigned long long run = 0, overflow = 0;
+    for (int r = 0; r < world; ++r) {
+        unsigned long long t = *reinterpret_cast<const unsigned long long *>(blocks + (size_t)r * (size_t)L.rank_stride + L.off_quads - 16);
+        if (t > (unsigned long long)L.quads_capacity) { // the shard outgrew its block: reported by vx_mesh_batch_info
+            overflow = 1;
+            t = (unsigned long long)L.quads_capacity;
+        }
+        off[r] = (uint32_t)run;
+        off[64 + r] = (uint32_t)t;
+        run += t;
+    }
+    if (run > cap_quads || run >= (1ull << 32)) overflow = 1;
+    cursor[0] = run;
+    cursor[1] = 0; // meshes: counted by the assemble kernel
+    cursor[2] = overflow;
+    cursor[3] = 0;
+}
+
+// one thread per quad of every rank's stream: move it to its place in the assembled stream
+__global__ void __launch_bounds__(256) copy_shard_quads_kernel(const uint8_t *__restrict__ blocks, VxShardLayout L, const uint32_t *__restrict__ off, uint8_t *dst,
+                                                               unsigned long long cap_quads) {
+    const int r = blockIdx.y;
+    const uint32_t n = off[64 + r], base = off[r];
+    const uint8_t *src = blocks + (size_t)r * (size_t)L.rank_stride + L.off_quads;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        if ((unsigned long long)base + q >= cap_quads) return;
+        const uint8_t a = src[3 * (size_t)q], b = src[3 * (size_t)q + 1], c = src[3 * (size_t)q + 2];
+        uint8_t *d = dst + 3 * ((size_t)base + q);
+        d[0] = a; d[1] = b; d[2] = c;
+    }
+}
+
 __global__ void __launch_bounds__(64) assemble_shards_kernel(int n_chunks, int world, ShardOffsets so, const uint8_t *__restrict__ blocks, VxShardLayout L,
                                                              uint32_t *quad_base, uint32_t *quad_count, uint32_t *slice_offsets, int32_t *face_aabb,
-                                                             uint8_t *has_mesh, unsigned long long *cursor, unsigned long long total) {
+                                                             uint8_t *has_mesh, unsigned long long *cursor, unsigned long long total,
+                                                             const uint32_t *__restrict__ d_off = nullptr) {
     const int c = blockIdx.x;
     if (c >= n_chunks) return;
     const int r = c % world;
@@ -573,10 +610,13 @@ __global__ void __launch_bounds__(64) assemble_shards_kernel(int n_chunks, int w
     const uint8_t *g_has = blk + L.off_has_mesh;
     for (int i = threadIdx.x; i < 198; i += 64) slice_offsets[(size_t)c * 198 + i] = g_so[j * 198 + i];
     if (threadIdx.x < 36) face_aabb[(size_t)c * 36 + threadIdx.x] = g_aabb[j * 36 + threadIdx.x];
-    if (threadIdx.x == 36) quad_base[c] = g_base[j] + so.off[r];
+    if (threadIdx.x == 36) quad_base[c] = g_base[j] + (d_off ? d_off[r] : so.off[r]);
     if (threadIdx.x == 37) quad_count[c] = g_count[j];
-    if (threadIdx.x == 38) has_mesh[c] = g_has[j];
-    if (c == 0 && threadIdx.x == 39) {
+    if (threadIdx.x == 38) {
+        has_mesh[c] = g_has[j];
+        if (d_off && g_has[j]) atomicAdd(cursor + 1, 1ull);
+    }
+    if (!d_off && c == 0 && threadIdx.x == 39) {
         cursor[0] = total;
         cursor[1] = 0;
         cursor[2] = 0;
@@ -967,6 +1007,7 @@ int vx_shard_layout(int32_t rows_per_rank, int64_t max_shard_quads, VxShardLayou
     out->off_slice_offsets = o; o = up16(o + 4 * 198 * rows);
     out->off_face_aabb = o; o = up16(o + 4 * 36 * rows);
     out->off_has_mesh = o; o = up16(o + rows);
+    o += 16; // block[off_quads - 16 .. off_quads - 8): u64 quad total of the shard (vx_mesh_shard_pack_async)
     out->off_quads = o; o = up16(o + 3 * max_shard_quads);
     out->quads_capacity = max_shard_quads;
     out->rank_stride = o;
@@ -1042,6 +1083,79 @@ int vx_mesh_batch_assemble_shards(VxContext *ctx, int32_t n_chunks, int32_t worl
     }
     b->total_quads = total;
     b->n_meshes = -1; // counted on demand (vx_mesh_batch_info)
+    *batch_inout = b;
+    return VX_OK;
+}
+
+// The same exchange without a host round trip (steady state of a re-mesh sweep: the block capacity is known from an earlier
+// sweep).  pack copies the whole quad section the block has room for and the shard's quad total (its cursor, 8 bytes in front
+// of the quad section); assemble reads the totals from the gathered blocks on the device.  A shard that outgrew its block
+// sets the batch's overflow flag: the next vx_mesh_batch_info fails with VX_ERR_CAPACITY and the caller sizes the blocks anew.
+int vx_mesh_shard_pack_async(VxContext *ctx, const VxMeshBatch *shard, const VxShardLayout *L, uint8_t *d_block) {
+    if (!ctx || !shard || !L || !d_block || shard->n_chunks > L->rows_per_rank) return vx_fail(ctx, VX_ERR_INVALID, "vx_mesh_shard_pack_async: bad argument");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)shard->n_chunks;
+    auto cp = [&](int64_t off, const void *src, size_t bytes) -> cudaError_t {
+        return bytes ? cudaMemcpyAsync(d_block + off, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream) : cudaSuccess;
+    };
+    VX_CUDA(ctx, cp(L->off_quad_base, shard->quad_base.ptr, 4 * n));
+    VX_CUDA(ctx, cp(L->off_quad_count, shard->quad_count.ptr, 4 * n));
+    VX_CUDA(ctx, cp(L->off_slice_offsets, shard->slice_offsets.ptr, 4 * 198 * n));
+    VX_CUDA(ctx, cp(L->off_face_aabb, shard->face_aabb.ptr, 4 * 36 * n));
+    VX_CUDA(ctx, cp(L->off_has_mesh, shard->has_mesh.ptr, n));
+    const int64_t q = shard->cap_quads < L->quads_capacity ? shard->cap_quads : L->quads_capacity;
+    VX_CUDA(ctx, cp(L->off_quads, shard->quads.ptr, 3 * (size_t)(q > 0 ? q : 0)));
+    VX_CUDA(ctx, cp(L->off_quads - 16, shard->cursor.ptr, sizeof(unsigned long long)));
+    return VX_OK;
+}
+
+int vx_mesh_batch_assemble_shards_async(VxContext *ctx, int32_t n_chunks, int32_t world, const uint8_t *d_blocks, const VxShardLayout *L,
+                                        const int32_t *d_positions, VxMeshBatch **batch_inout) {
+    if (!ctx || !batch_inout || !L || n_chunks < 0 || world < 1 || world > 64 || (int64_t)L->rows_per_rank * world < n_chunks || (n_chunks > 0 && !d_blocks))
+        return vx_fail(ctx, VX_ERR_INVALID, "vx_mesh_batch_assemble_shards_async: bad argument");
+    VX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t bound = (int64_t)world * L->quads_capacity; // the assembled stream can never need more
+    if (bound >= (int64_t)1 << 32) return vx_fail(ctx, VX_ERR_CAPACITY, "more than 2^32 quads in one batch");
+    VxMeshBatch *b = *batch_inout;
+    const bool fresh = b == nullptr;
+    if (!fresh && b->n_chunks != n_chunks) return vx_fail(ctx, VX_ERR_INVALID, "batch was created for another chunk count");
+    if (fresh) {
+        b = new VxMeshBatch();
+        int rc = batch_alloc(ctx, b, n_chunks, bound > 0 ? bound : 1);
+        if (rc != VX_OK) { vx_mesh_batch_release(ctx, b); return rc; }
+    } else if (bound > b->cap_quads) {
+        VX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        VX_CUDA(ctx, b->quads.reserve(3 * (size_t)bound + 16));
+        b->cap_quads = bound;
+    }
+    cudaError_t e = ctx->tmp_d.reserve(sizeof(uint32_t) * 128);
+    if (e == cudaSuccess && n_chunks > 0) {
+        if (d_positions) e = cudaMemcpyAsync(b->positions.ptr, d_positions, sizeof(int32_t) * 3 * (size_t)n_chunks, cudaMemcpyDeviceToDevice, ctx->stream);
+        else if (fresh) e = cudaMemsetAsync(b->positions.ptr, 0, sizeof(int32_t) * 3 * (size_t)n_chunks, ctx->stream);
+    }
+    if (e == cudaSuccess) {
+        uint32_t *d_off = ctx->tmp_d.as<uint32_t>();
+        shard_offsets_kernel<<<1, 32, 0, ctx->stream>>>(world, d_blocks, *L, d_off, b->cursor.as<unsigned long long>(), (unsigned long long)b->cap_quads);
+        ctx->launches++;
+        if (n_chunks > 0) {
+            ShardOffsets none;
+            memset(&none, 0, sizeof(none));
+            assemble_shards_kernel<<<n_chunks, 64, 0, ctx->stream>>>(n_chunks, world, none, d_blocks, *L, b->quad_base.as<uint32_t>(), b->quad_count.as<uint32_t>(),
+                                                                     b->slice_offsets.as<uint32_t>(), b->face_aabb.as<int32_t>(), b->has_mesh.as<uint8_t>(),
+                                                                     b->cursor.as<unsigned long long>(), 0ull, d_off);
+            ctx->launches++;
+            const int per_rank = (int)((L->quads_capacity + 255) / 256 < 1 ? 1 : ((L->quads_capacity + 255) / 256 > 1024 ? 1024 : (L->quads_capacity + 255) / 256));
+            copy_shard_quads_kernel<<<dim3(per_rank, world), 256, 0, ctx->stream>>>(d_blocks, *L, d_off, b->quads.as<uint8_t>(), (unsigned long long)b->cap_quads);
+            ctx->launches++;
+        }
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        if (fresh) vx_mesh_batch_release(ctx, b);
+        return vx_cuda_fail(ctx, e, "assemble shards (async)", __FILE__, __LINE__);
+    }
+    b->total_quads = -1; // read from the device on demand (vx_mesh_batch_info), together with the overflow flag
+    b->n_meshes = -1;
     *batch_inout = b;
     return VX_OK;
 }

@@ -257,13 +257,30 @@ class MeshShardExchange:
         self.mine = torch.zeros(1, dtype=torch.int64, device=device)
         self.stream = torch.cuda.ExternalStream(ctx.stream, device=device)
 
-    def sweep(self, d_voxels: int, d_positions: int, d_neighbors: int, d_uniform_flags: int = 0) -> api.MeshBatch:
-        """Re-mesh this rank's shard and rebuild the full batch on every rank.  Returns the full batch."""
+    def sweep(self, d_voxels: int, d_positions: int, d_neighbors: int, d_uniform_flags: int = 0, host_sync: Optional[bool] = None) -> api.MeshBatch:
+        """Re-mesh this rank's shard and rebuild the full batch on every rank.  Returns the full batch.
+        The first sweep reads the ragged shard sizes back to size the exchange blocks (two host round trips); later sweeps
+        (host_sync=None / False) run without one: mesh kernel -> pack (the block carries the shard's quad total) -> one
+        NCCL all-gather -> assemble from the totals on the device.  A shard that outgrows its block makes the next
+        .info() of the full batch fail with VX_ERR_CAPACITY: call sweep(..., host_sync=True) once to size the blocks anew
+        (check() does that check for you)."""
         import torch
         import torch.distributed as dist
         ctx, lib = self.ctx, self.ctx.lib
         self.shard = api.BinaryGreedyMesher.mesh_batch_subset(d_voxels, d_positions, d_neighbors, d_uniform_flags, self.n, self.d_ids.data_ptr(),
                                                               int(self.ids.size), ctx, batch=self.shard)
+        if host_sync is None:
+            host_sync = self.block is None or self.full is None
+        if not host_sync:
+            ctx.check(lib.vx_mesh_shard_pack_async(ctx.handle, self.shard.handle, C.byref(self.layout), C.c_void_p(self.block.data_ptr())))
+            with torch.cuda.stream(self.stream):
+                self._all_gather(self.blocks, self.block)  # NCCL over NVLink
+            h = C.c_void_p(self.full.handle.value)
+            ctx.check(lib.vx_mesh_batch_assemble_shards_async(ctx.handle, self.n, self.world, C.c_void_p(self.blocks.data_ptr()), C.byref(self.layout),
+                                                              C.c_void_p(d_positions) if d_positions else None, C.byref(h)))
+            self.full._host = None
+            self.exchanged_bytes = int(self.layout.rank_stride) * self.world
+            return self.full
         my_quads = int(self.shard.info().total_quads)  # synchronises: the ragged sizes have to be known to size the exchange
         with torch.cuda.stream(self.stream):
             self.mine.fill_(my_quads)
@@ -286,6 +303,14 @@ class MeshShardExchange:
         self.full._host = None
         self.exchanged_bytes = int(self.layout.rank_stride) * self.world
         return self.full
+
+    def check(self) -> bool:
+        """After sweeps without host round trips: True if every shard fitted its block (synchronises)."""
+        try:
+            self.full.info()
+            return True
+        except api.VxError:
+            return False
 
     def _all_gather(self, out, inp):
         import torch

@@ -300,6 +300,15 @@ VX_API int vx_mesh_shard_pack(VxContext *ctx, const VxMeshBatch *shard, const Vx
 VX_API int vx_mesh_batch_assemble_shards(VxContext *ctx, int32_t n_chunks, int32_t world, const uint8_t *d_blocks,
                                   const VxShardLayout *layout, const int64_t *shard_quads, const int32_t *d_positions,
                                   VxMeshBatch **batch_inout);
+/* The same exchange without a host round trip, for the steady state of a re-mesh sweep (block capacity known from an
+ * earlier sweep): _pack_async copies the whole quad section the block has room for plus the shard's quad total (a u64 at
+ * off_quads - 16 of the block); _assemble_shards_async reads the totals from the gathered blocks on the device, so nothing
+ * is read back between the mesh kernel, the all-gather and the assembled batch.  A shard that outgrew its block sets the
+ * batch's overflow flag: the next vx_mesh_batch_info on the assembled batch fails with VX_ERR_CAPACITY and the caller goes
+ * through the synchronous pair once to size the blocks anew. */
+VX_API int vx_mesh_shard_pack_async(VxContext *ctx, const VxMeshBatch *shard, const VxShardLayout *layout, uint8_t *d_block);
+VX_API int vx_mesh_batch_assemble_shards_async(VxContext *ctx, int32_t n_chunks, int32_t world, const uint8_t *d_blocks,
+                                        const VxShardLayout *layout, const int32_t *d_positions, VxMeshBatch **batch_inout);
 VX_API void vx_mesh_batch_release(VxContext *ctx, VxMeshBatch *b);
 
 /* BinaryGreedyMesher::greedy_mesh_slice (binary_greedy.rs:675) for n_slices masks of 32 rows.
