@@ -325,8 +325,8 @@ def run_cuda(args):
         if comps is None:
             api.render_frame_device(batch, vp_t, cam_t, cfg_lanes if in_flight > 1 else cfg_async, VD, lanes[l])
         else:
-            # hand-off fused into the raster kernels: every rank's last CTA publishes its stripe, GPU0's last CTA waits for all
-            # of them and hands the buffer back -- three launches per rank and frame, none of them a hand-off kernel
+            # the hand-off rides in the frame's own launch graph: the setup kernel waits for the acknowledgement, a 1-thread node
+            # behind the raster kernel publishes the stripe, GPU0's raster kernel waits for all of them and hands the buffer back
             k = lane_frame_no[l]
             fused = comps[l].render(batch, vp_t, cam_t, cfg_stripe_lanes if in_flight > 1 else cfg, VD, k,
                                     compose_release=k if rank == 0 else None)

@@ -138,8 +138,9 @@ class StripeCompositor:
         arrive = self.arrive + 4 * FLAG_STRIDE_WORDS * self.rank
         wait_needed = frame_no >= self.n_buffers  # the buffer is free once dst has consumed frame_no - n_buffers
         if rows > 0:
-            # hand-off fused into the raster kernel: it waits for the acknowledgement before its first store into the frame
-            # and its last CTA publishes the arrival word -- three launches per stripe, none of them a hand-off kernel.
+            # the hand-off rides in the frame's own kernels: the setup kernel waits for the acknowledgement, the arrival word is
+            # published behind the raster kernel (or by its last CTA: fused_signal), the composing GPU's raster kernel waits
+            # for all arrivals and hands an older buffer back -- one launch graph per frame and rank, no collective.
             # (The ctypes objects are kept between calls: at tens of thousands of frames per second the host side of a frame
             # has to stay in the single-digit microseconds.)
             st = self._call_state

@@ -384,7 +384,7 @@ VX_API int vx_render_frame_into(VxContext *ctx, const VxMeshBatch *batch, const 
                          uint32_t *d_color_dst, float *d_depth_dst);
 /* Stripe of a frame that is composed on another GPU (one process per GPU; framebuffer.rs:392-431 hands disjoint
  * `&mut` stripes of ONE framebuffer to the workers): as vx_render_frame_into with d_color_dst / d_depth_dst pointing
- * into the peer-mapped frame (vx_ipc_open), plus the hand-off fused into the raster kernel -- before its first store
+ * into the peer-mapped frame (vx_ipc_open), plus the hand-off inside the frame's own kernels -- before its first store
  * the kernel waits until *d_wait_flag (a word in THIS GPU's memory, written by the composing GPU when it has consumed
  * the frame that last used the buffer) has reached wait_value; after its last store the last CTA publishes signal_value
  * into *d_signal_flag (the composing GPU's arrival word for this rank) with release semantics at system scope.  Either
