@@ -97,3 +97,36 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0, out.stderr
     assert out.stdout.split() == ["1280", "720", "128", "72", str(0xFF007D00), "80", "224"]
+
+
+def test_ctypes_structs_match_the_c_layout_field_by_field(tmp_path):
+    """Every struct that crosses the ABI by pointer: sizeof and the offset of each field as the C compiler sees them in
+    include/vx_b200.h equal the ctypes declarations in _lib.py (names included) -- a reordered or resized field on either
+    side would otherwise corrupt a call silently."""
+    import subprocess
+    from differential_projection_voxel_renderer_b200 import _lib
+    structs = ["VxFrameConfig", "VxStripeSync", "VxShardLayout", "VxMeshBatchInfo", "VxFrameStats", "VxTerrainParams", "VxMeshBatchDevice"]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vx_b200.h"', "int main(void) {"]
+    for sname in structs:
+        cls = getattr(_lib, sname)
+        lines.append(f'    printf("{sname} %zu", sizeof({sname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'    printf(" {fname}:%zu", offsetof({sname}, {fname}));')
+        lines.append('    printf("\\n");')
+    lines += ["    return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    seen = {}
+    for row in out.stdout.strip().splitlines():
+        parts = row.split()
+        seen[parts[0]] = (int(parts[1]), {kv.split(":")[0]: int(kv.split(":")[1]) for kv in parts[2:]})
+    for sname in structs:
+        cls = getattr(_lib, sname)
+        size, offs = seen[sname]
+        assert ctypes.sizeof(cls) == size, sname
+        for fname, _ in cls._fields_:
+            assert getattr(cls, fname).offset == offs[fname], f"{sname}.{fname}"
