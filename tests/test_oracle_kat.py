@@ -205,6 +205,9 @@ def test_shading_constants(ob):
     cfg = ob.default_frame_config(64, 64)
     fps = [int(ob.lib().vxo_face_light(__import__("ctypes").byref(cfg), f) * 256.0) for f in range(6)]
     assert fps == [148, 89, 237, 89, 134, 89]
+    # tests/shading_tests.rs:8-37 (test_shading_brighter_when_facing_light): with the default light a face looking up
+    # (PosY, face 2) is brighter than one looking down (NegY, face 3) -- and nothing falls below the ambient floor
+    assert fps[2] > fps[3] and min(fps) == int(cfg.ambient * 256.0)
     assert ob.lib().vxo_shade_color_u32(0xFFFFFFFF, 1.0) == 0xFFFFFFFF
     assert ob.lib().vxo_shade_color_u32(0xFF808080, 0.5) == 0xFF404040
 
